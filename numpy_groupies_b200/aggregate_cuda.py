@@ -1,0 +1,580 @@
+"""``aggregate_cuda`` -- the B200 implementation of numpy-groupies' ``aggregate``.
+
+A sixth implementation module next to the reference's aggregate_numpy / aggregate_numba /
+aggregate_pandas ...: same signature, same Forms 1-5, same dtype / fill_value / exception
+rules (``_semantics.py`` restates utils.py), but the per-function kernel layer
+(aggregate_numpy.py:20-274) is a set of hand-written sm_100a CUDA kernels reached through
+the C ABI of ``csrc/libaggcuda.so`` (include/aggcuda.h).  PyTorch is used for device
+buffers and streams only.  There is no CPU fallback: without the shared library or without
+a CUDA device every call raises.
+
+Inputs may be numpy arrays / sequences / scalars (copied to the device, result returned as a
+numpy array -- what the reference's test-suite does) or CUDA ``torch.Tensor``s (result is a
+CUDA tensor; nothing crosses PCIe except the 32-byte status record).
+
+Extra keyword arguments beyond the reference's (it already takes ``**kwargs``):
+  check=True          read the device status record after the call (one stream sync) and raise
+                      ValueError for bad labels, as the reference does.  ``check=False`` keeps the
+                      call asynchronous; bad labels are then ignored silently.
+  assume_sorted=False promise non-decreasing flat labels (N->N functions skip the sort; verified).
+  fast=True           allow the shared-memory fast kernels (False forces the general path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi, _semantics as sem
+
+__all__ = ["aggregate", "unpack"]
+
+_torch = None
+
+
+def _t():
+    global _torch
+    if _torch is None:
+        import torch
+        _torch = torch
+    return _torch
+
+
+def _require_cuda():
+    torch = _t()
+    if not torch.cuda.is_available():
+        raise RuntimeError("aggregate_cuda needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+# numpy dtype name -> torch dtype used to *carry* the bytes (unsigned types travel as same-width signed)
+_CARRIER = {"bool": "bool", "int8": "int8", "uint8": "uint8", "int16": "int16", "uint16": "int16",
+            "int32": "int32", "uint32": "int32", "int64": "int64", "uint64": "int64",
+            "float32": "float32", "float64": "float64"}
+_SIGNED_VIEW = {"uint16": np.int16, "uint32": np.int32, "uint64": np.int64}
+
+
+class _Dev:
+    """A device buffer plus the numpy dtype its bytes mean."""
+    __slots__ = ("t", "dtype")
+
+    def __init__(self, t, dtype):
+        self.t, self.dtype = t, np.dtype(dtype)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() if self.t.numel() else 0
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _tensor_np_dtype(t):
+    return np.dtype(str(t.dtype).split(".")[-1])
+
+
+def _upload(arr, device):
+    """numpy array -> contiguous device buffer (H2D copy)."""
+    torch = _t()
+    arr = np.ascontiguousarray(arr)
+    dt = arr.dtype
+    view = arr.view(_SIGNED_VIEW[dt.name]) if dt.name in _SIGNED_VIEW else arr
+    return _Dev(torch.from_numpy(view).to(device, non_blocking=False), dt)
+
+
+def _from_tensor(t):
+    dt = _tensor_np_dtype(t)
+    return _Dev(t.contiguous(), dt)
+
+
+def _empty(n, dtype, device):
+    torch = _t()
+    return _Dev(torch.empty(int(n), dtype=getattr(torch, _CARRIER[np.dtype(dtype).name]), device=device), dtype)
+
+
+def _download(dev, shape=None):
+    arr = dev.t.cpu().numpy()
+    if dev.dtype.name in _SIGNED_VIEW:
+        arr = arr.view(dev.dtype)
+    return arr if shape is None else arr.reshape(shape)
+
+
+def _as_user_tensor(dev):
+    torch = _t()
+    if dev.dtype.name in _SIGNED_VIEW and hasattr(torch, dev.dtype.name):
+        return dev.t.view(getattr(torch, dev.dtype.name))
+    return dev.t
+
+
+# ------------------------------------------------------------------------------------------------
+# request assembly
+# ------------------------------------------------------------------------------------------------
+_DEVICE_OPS = {"sum", "prod", "len", "last", "first", "all", "any", "min", "max", "argmax", "argmin", "mean",
+               "sumofsquares", "var", "std", "allnan", "anynan", "cumsum", "cumprod", "cummax", "cummin", "sort"}
+_N_TO_N = {"cumsum", "cumprod", "cummax", "cummin", "sort"}
+_COMPUTE_AS = {"float16": np.float32}          # dtypes the kernels do not load natively
+
+
+class _Call:
+    """Everything decided on the host before any kernel runs."""
+    pass
+
+
+def _np_dtype_of_scalar(a):
+    return np.dtype(type(a))
+
+
+def _fill_numbers(fill_value, out_dtype):
+    """(double, int64, is_nan) views of fill_value for the finalise kernel."""
+    try:
+        f = float(fill_value)
+    except (TypeError, ValueError):
+        f = 0.0
+    nan = isinstance(fill_value, (float, np.floating)) and math.isnan(fill_value)
+    if np.issubdtype(out_dtype, np.floating):
+        i = 0
+    else:
+        try:
+            i = int(np.asarray(fill_value).astype(out_dtype if out_dtype != np.dtype(bool) else np.int64))
+            if out_dtype == np.dtype(bool):
+                i = int(bool(fill_value))
+        except (ValueError, OverflowError):
+            i = 0
+        if i >= 2 ** 63:
+            i -= 2 ** 64
+    return f, i, nan
+
+
+def _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, kwargs, resolve_size):
+    """Host-only planning: validates like the reference and decides op / dtypes / index form.
+    ``resolve_size(plan, labels)`` supplies the label maxima when ``size`` is None."""
+    c = _Call()
+    c.check = kwargs.pop("check", True)
+    c.assume_sorted = bool(kwargs.pop("assume_sorted", False))
+    c.fast = bool(kwargs.pop("fast", True))
+
+    # --- what kind of inputs ------------------------------------------------------------------
+    c.device_mode = _is_tensor(group_idx) or _is_tensor(a)
+    if c.device_mode:
+        torch = _t()
+        if not _is_tensor(group_idx):
+            group_idx = torch.as_tensor(np.asanyarray(group_idx), device=a.device)
+        g_shape, g_dtype = tuple(group_idx.shape), _tensor_np_dtype(group_idx)
+        if _is_tensor(a):
+            a_scalar, a_shape, a_dtype = (a.ndim == 0), tuple(a.shape), _tensor_np_dtype(a)
+            if a_scalar:
+                a = a.item()
+                a_dtype = _np_dtype_of_scalar(a)
+        else:
+            a_scalar = isinstance(a, (int, float, complex)) or np.ndim(a) == 0
+            if not a_scalar:
+                a = torch.as_tensor(np.asanyarray(a), device=group_idx.device)
+                a_shape, a_dtype = tuple(a.shape), _tensor_np_dtype(a)
+            else:
+                a_shape, a_dtype = (), _np_dtype_of_scalar(a if isinstance(a, (int, float, complex)) else a.item())
+    else:
+        if not isinstance(a, (int, float, complex)):
+            a = np.asanyarray(a)
+        group_idx = np.asanyarray(group_idx)
+        g_shape, g_dtype = group_idx.shape, group_idx.dtype
+        a_scalar = isinstance(a, (int, float, complex)) or a.ndim == 0
+        a_shape = () if a_scalar else a.shape
+        if isinstance(a, (int, float, complex)):
+            a_dtype = _np_dtype_of_scalar(a)
+        else:
+            a_dtype = a.dtype
+            if a_scalar:                                   # 0-d array: behave like the python scalar
+                a = a.item()
+    c.group_idx, c.a, c.a_scalar, c.a_dtype, c.a_shape = group_idx, a, a_scalar, np.dtype(a_dtype), a_shape
+
+    # --- Forms ---------------------------------------------------------------------------------
+    plan = sem.plan_index(g_shape, np.issubdtype(g_dtype, np.integer), a_shape, a_scalar, size, order, axis, func)
+    if plan.needs_size:
+        resolve_size(plan, c)
+    c.plan, c.order = plan, order
+
+    # --- function ------------------------------------------------------------------------------
+    name = sem.canonical_func(func)
+    c.name = name
+    if not isinstance(name, str):
+        c.kind = "callable"
+        c.user_dtype = dtype
+        c.fill_value = fill_value
+        return c
+    nan_form = name.startswith("nan")
+    base = name[3:] if nan_form else name
+    c.base, c.nan_form = base, nan_form
+    if nan_form and a_scalar:
+        raise ValueError("nan-version not supported for scalar input.")
+    if np.issubdtype(c.a_dtype, np.complexfloating):
+        raise NotImplementedError("complex input is not supported by aggregate_cuda")
+
+    n_for_dtype = plan.flat_size if base not in ("cumprod", "cummax", "cummin") else plan.n
+    user_dtype = None if dtype is None else np.dtype(dtype)
+    dtype_k = sem.result_dtype(user_dtype, name, c.a_dtype, a_scalar, n_for_dtype)
+    sem.validate_fill(fill_value, dtype_k, name)
+    c.fill_value = fill_value
+
+    if base == "array":
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)} for func 'array'")
+        if fill_value is not None and not (np.isscalar(fill_value) or len(fill_value) == 0):
+            raise ValueError("fill_value must be None, a scalar or an empty sequence")
+        c.kind = "array"
+        return c
+
+    # keyword arguments the reference's kernels accept
+    c.ddof, c.reverse = 0, False
+    if base in ("var", "std"):
+        c.ddof = kwargs.pop("ddof", 0)
+    elif base == "sort":
+        c.reverse = bool(kwargs.pop("reverse", False))
+    if kwargs:
+        raise TypeError(f"{name}() got unexpected keyword arguments {sorted(kwargs)}")
+
+    if base in ("mean", "var", "std") and a_scalar:
+        raise ValueError("cannot take mean / variance with scalar a")
+    out_dtype = sem.kernel_out_dtype(name, dtype_k, c.a_dtype, fill_value)
+    flags = _abi.F_NANSKIP if nan_form else 0
+    if base in ("min", "max"):
+        sem.extreme_identity_check(name, fill_value, dtype_k)
+        sem.probe_fill(fill_value, out_dtype)
+    elif base in ("argmin", "argmax"):
+        if not nan_form:                                   # nanarg* first maps a to float (np.where(isnan..))
+            sem.extreme_identity_check(name, np.nan, c.a_dtype)
+        sem.probe_fill(fill_value, out_dtype)
+    elif base in ("first", "last", "prod"):
+        sem.probe_fill(fill_value, out_dtype)
+    if base in ("sum", "len", "sumofsquares") and fill_value != 0:
+        flags |= _abi.F_NEED_TOUCHED
+    if base == "prod" and fill_value != 1:
+        flags |= _abi.F_NEED_TOUCHED
+    if base == "std":
+        flags |= _abi.F_SQRT
+    if base == "sort" and c.reverse:
+        flags |= _abi.F_REVERSE
+    if base in ("cumsum",):
+        # the reference's in-place `run -= ...; run += a[...]` (aggregate_numpy.py:262-265) raises numpy's
+        # TypeError for bool arithmetic and UFuncTypeError (a TypeError) for non same-kind casts
+        if dtype_k == np.dtype(bool):
+            raise TypeError("numpy boolean subtract, the `-` operator, is not supported (cumsum of bool)")
+        mixed = np.result_type(dtype_k, c.a_dtype)
+        if not np.can_cast(mixed, dtype_k, "same_kind"):
+            raise TypeError(f"Cannot cast ufunc 'add' output from {mixed} to {dtype_k} with casting rule 'same_kind'")
+    if isinstance(fill_value, (float, np.floating)) and math.isnan(fill_value):
+        flags |= _abi.F_FILL_NAN
+    if c.assume_sorted:
+        flags |= _abi.F_ASSUME_SORTED
+    if not c.fast:
+        flags |= _abi.F_NO_FAST
+    if out_dtype == np.dtype(object) or out_dtype.name not in _abi.DT and out_dtype.name != "float16":
+        raise NotImplementedError(f"output dtype {out_dtype} is not supported by aggregate_cuda")
+    if base in _N_TO_N and plan.ndim_idx > 1 and int(np.prod(plan.out_shape, dtype=np.int64)) != plan.n:
+        # N->N result cannot be reshaped to the group grid (reference: reshape error, aggregate_numpy.py:366)
+        raise ValueError(f"cannot reshape array of size {plan.n} into shape {tuple(plan.out_shape)}")
+    c.kind = "device"
+    c.flags, c.out_dtype, c.dtype_k = flags, out_dtype, dtype_k
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# execution
+# ------------------------------------------------------------------------------------------------
+def _device_of(c):
+    torch = _require_cuda()
+    for x in (c.group_idx, c.a):
+        if _is_tensor(x):
+            if not x.is_cuda:
+                raise ValueError("torch inputs must live on a CUDA device")
+            return x.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr(device):
+    return _t().cuda.current_stream(device).cuda_stream
+
+
+def _labels_on_device(c, device):
+    if getattr(c, "_labels_dev", None) is None:
+        g = c.group_idx
+        c._labels_dev = _from_tensor(g) if _is_tensor(g) else _upload(g, device)
+    return c._labels_dev
+
+
+def _resolve_size_device(plan, c):
+    """size=None: measure the label maxima with agc_label_minmax (utils.py:515-526 does np.max)."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    device = _device_of(c)
+    lab = _labels_on_device(c, device)
+    rows = plan.extra.get("rows", 1) if plan.form == "multi" else 1
+    per_row = lab.t.numel() // max(rows, 1)
+    if per_row == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    mm = torch.empty((rows, 2), dtype=torch.int64, device=device)
+    es = lab.dtype.itemsize
+    with torch.cuda.device(device):
+        for r in range(rows):
+            rc = lib.agc_label_minmax(lab.ptr + r * per_row * es, _abi.dtype_code(lab.dtype), per_row,
+                                      mm.data_ptr() + r * 16, _stream_ptr(device))
+            if rc:
+                raise RuntimeError(_abi.last_error())
+    mm = mm.cpu().numpy()
+    if (mm[:, 0] < 0).any():
+        raise ValueError("negative indices not supported")
+    if plan.form == "flat":
+        plan.flat_size = int(mm[0, 1]) + 1
+    elif plan.form == "axis":
+        sem.finish_axis_plan(plan, int(mm[0, 1]) + 1)
+    else:
+        sem.finish_multi_plan(plan, [int(v) + 1 for v in mm[:, 1]])
+
+
+def _build_index(c, lab):
+    plan = c.plan
+    ix = _abi.Index()
+    ix.form = {"flat": _abi.FORM_FLAT, "axis": _abi.FORM_AXIS, "multi": _abi.FORM_MULTI}[plan.form]
+    ix.dtype = _abi.dtype_code(lab.dtype)
+    ix.labels = lab.ptr
+    if plan.form != "flat":
+        nd = len(plan.dims)
+        if nd > _abi.MAX_NDIM:
+            raise NotImplementedError(f"more than {_abi.MAX_NDIM} dimensions are not supported")
+        ix.ndim, ix.axis, ix.axis_size = nd, plan.axis, plan.axis_size
+        for d in range(nd):
+            ix.dims[d], ix.strides[d] = plan.dims[d], plan.strides[d]
+    return ix
+
+
+def _values_on_device(c, device):
+    if c.a_scalar:
+        return None
+    a = c.a
+    if _is_tensor(a):
+        dev = _from_tensor(a)
+        if dev.dtype.name in _COMPUTE_AS:
+            dev = _Dev(dev.t.to(_t().float32), np.float32)
+        dev.t = dev.t.reshape(-1)
+        return dev
+    arr = np.ascontiguousarray(a)
+    if arr.dtype.name in _COMPUTE_AS:
+        arr = arr.astype(_COMPUTE_AS[arr.dtype.name])
+    return _upload(arr.reshape(-1), device)
+
+
+def _run_device(c):
+    torch = _require_cuda()
+    lib = _abi.load()
+    device = _device_of(c)
+    plan = c.plan
+    lab = _labels_on_device(c, device)
+    vals = _values_on_device(c, device)
+    base = c.base
+    n_out = plan.n if base in _N_TO_N else plan.flat_size
+    out_np_dtype = c.out_dtype
+    compute_out = np.dtype(_COMPUTE_AS.get(out_np_dtype.name, out_np_dtype))
+
+    req = _abi.Request()
+    req.op = _abi.OP[base]
+    req.flags = c.flags
+    a_dt = np.dtype(_COMPUTE_AS.get(c.a_dtype.name, c.a_dtype))
+    req.a_dtype = _abi.dtype_code(a_dt)
+    req.out_dtype = _abi.dtype_code(compute_out)
+    if vals is None:
+        req.a = None
+        req.a_scalar_f64 = float(c.a)
+        req.a_scalar_i64 = int(c.a) if not isinstance(c.a, (float, np.floating)) else 0
+    else:
+        req.a = vals.ptr
+    req.index = _build_index(c, lab)
+    req.n, req.size = plan.n, plan.flat_size
+    f64, i64, _ = _fill_numbers(c.fill_value, compute_out)
+    req.fill_f64, req.fill_i64 = f64, i64
+    req.ddof = float(c.ddof)
+    req.index_base = 0
+    req.arg_stride, req.arg_len = plan.arg_stride, plan.arg_len
+
+    with torch.cuda.device(device):
+        out = _empty(n_out, compute_out, device)
+        status = torch.zeros(8, dtype=torch.int32, device=device)
+        req.out = out.ptr
+        req.status = status.data_ptr()
+        ws_bytes = lib.agc_workspace_bytes(C.byref(req))
+        if ws_bytes < 0:
+            raise RuntimeError(_abi.last_error())
+        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
+        req.workspace, req.workspace_bytes = ws.data_ptr(), ws_bytes
+        rc = lib.agc_aggregate(C.byref(req), _stream_ptr(device))
+        if rc:
+            msg = _abi.last_error()
+            if rc == -20:
+                raise NotImplementedError(msg)
+            raise RuntimeError(f"agc_aggregate failed ({rc}): {msg}")
+        if c.check:
+            st = status.cpu().numpy()
+            if st[_abi.ST_BADLABEL]:
+                raise ValueError("group_idx contains negative indices or indices too large for size")
+            if st[_abi.ST_UNSORTED]:
+                raise ValueError("assume_sorted=True but group_idx is not sorted")
+            c.regime = int(st[_abi.ST_REGIME])
+    if out_np_dtype != compute_out:                         # float16 results
+        out = _Dev(out.t.to(getattr(torch, out_np_dtype.name)), out_np_dtype)
+    return out
+
+
+def _finish_shape_np(c, arr):
+    plan = c.plan
+    if plan.ndim_idx > 1:
+        shape = plan.out_shape
+        if int(np.prod(shape, dtype=np.int64)) != arr.size:
+            raise ValueError(f"cannot reshape array of size {arr.size} into shape {tuple(shape)}")
+        arr = arr.reshape(shape, order=c.order)
+    return arr
+
+
+def _finish_shape_torch(c, t):
+    plan = c.plan
+    if plan.ndim_idx > 1:
+        shape = tuple(plan.out_shape)
+        if int(np.prod(shape, dtype=np.int64)) != t.numel():
+            raise ValueError(f"cannot reshape tensor of size {t.numel()} into shape {shape}")
+        if c.order == "F":
+            t = t.reshape(shape[::-1]).permute(*range(len(shape) - 1, -1, -1))
+        else:
+            t = t.reshape(shape)
+    return t
+
+
+def _group_order(c):
+    """Stable device sort of element positions by flat group: (order[n], offsets[size+1]) as numpy."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    device = _device_of(c)
+    plan = c.plan
+    lab = _labels_on_device(c, device)
+    ix = _build_index(c, lab)
+    with torch.cuda.device(device):
+        order = torch.empty(plan.n, dtype=torch.int64, device=device)
+        offsets = torch.empty(plan.flat_size + 1, dtype=torch.int64, device=device)
+        status = torch.zeros(8, dtype=torch.int32, device=device)
+        ws_bytes = lib.agc_group_order_workspace_bytes(plan.n, plan.flat_size)
+        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
+        rc = lib.agc_group_order(C.byref(ix), plan.n, plan.flat_size, order.data_ptr(), offsets.data_ptr(),
+                                 ws.data_ptr(), ws_bytes, status.data_ptr(), _stream_ptr(device))
+        if rc:
+            msg = _abi.last_error()
+            if rc == -20:
+                raise NotImplementedError(msg)
+            raise RuntimeError(f"agc_group_order failed ({rc}): {msg}")
+        if status.cpu().numpy()[_abi.ST_BADLABEL]:
+            raise ValueError("group_idx contains negative indices or indices too large for size")
+    return order, offsets
+
+
+def _host_values(c):
+    if c.a_scalar:
+        raise ValueError("scalar a is not supported for this function")
+    a = c.a
+    arr = a.detach().cpu().numpy() if _is_tensor(a) else np.asarray(a)
+    return arr.reshape(-1)
+
+
+def _run_array(c):
+    """func='array' (aggregate_numpy.py:217-227): grouping order from the device radix sort, the
+    object array itself can only live on the host."""
+    order, offsets = _group_order(c)
+    vals = _host_values(c)
+    order, offsets = order.cpu().numpy(), offsets.cpu().numpy()
+    pieces = np.split(vals[order], offsets[1:-1])
+    ret = np.asanyarray(pieces, dtype="object") if len(pieces) != 1 else _one_group_object(pieces)
+    fill = c.fill_value
+    if fill is None or np.isscalar(fill):
+        counts = np.diff(offsets)
+        ret[counts == 0] = fill
+    return ret
+
+
+def _one_group_object(pieces):
+    ret = np.empty(1, dtype=object)
+    ret[0] = pieces[0]
+    return np.asanyarray(pieces, dtype="object")
+
+
+def _run_callable(c):
+    """Arbitrary per-group callables (aggregate_numpy.py:230-241): device sort, host loop."""
+    order, offsets = _group_order(c)
+    vals = _host_values(c)
+    order, offsets = order.cpu().numpy(), offsets.cpu().numpy()
+    sorted_vals = vals[order]
+    ret = np.full(c.plan.flat_size, c.fill_value, dtype=c.user_dtype or np.float64)
+    for g in range(c.plan.flat_size):
+        lo, hi = offsets[g], offsets[g + 1]
+        if hi > lo:
+            ret[g] = c.name(sorted_vals[lo:hi])
+    return ret
+
+
+def aggregate(group_idx, a, func="sum", size=None, fill_value=0, order="C", dtype=None, axis=None, **kwargs):
+    """Group-wise reduction / scan of ``a`` by the integer labels ``group_idx`` on a B200.
+
+    Same contract as ``numpy_groupies.aggregate_numpy.aggregate`` (aggregate_numpy.py:370-392;
+    parameters documented in utils.py:6-56): Forms 1-5 of ``group_idx``/``a``, ``func`` as string,
+    builtin, numpy function or arbitrary callable, ``size``, ``fill_value``, ``order``, ``dtype``,
+    ``axis``, plus ``ddof`` (var/std) and ``reverse`` (sort).
+    """
+    c = _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, dict(kwargs), _resolve_size_device)
+    if c.kind == "device":
+        out = _run_device(c)
+        if c.device_mode:
+            return _finish_shape_torch(c, _as_user_tensor(out))
+        return _finish_shape_np(c, _download(out))
+    if c.kind == "array":
+        ret = _run_array(c)
+    else:
+        ret = _run_callable(c)
+    return _finish_shape_np(c, ret)
+
+
+def unpack(group_idx, ret):
+    """``ret[group_idx]`` on the device (utils.py:548-553)."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    device_mode = _is_tensor(group_idx) or _is_tensor(ret)
+    device = (group_idx.device if _is_tensor(group_idx) else ret.device) if device_mode else torch.device("cuda", torch.cuda.current_device())
+    lab = _from_tensor(group_idx) if _is_tensor(group_idx) else _upload(np.asanyarray(group_idx), device)
+    tab = _from_tensor(ret) if _is_tensor(ret) else _upload(np.asanyarray(ret), device)
+    n = lab.t.numel()
+    out = _empty(n, tab.dtype, device)
+    status = torch.zeros(8, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        rc = lib.agc_unpack(tab.ptr, tab.dtype.itemsize, tab.t.numel(), lab.ptr, _abi.dtype_code(lab.dtype), n,
+                            out.ptr, status.data_ptr(), _stream_ptr(device))
+        if rc:
+            raise RuntimeError(_abi.last_error())
+        if status.cpu().numpy()[_abi.ST_BADLABEL]:
+            raise IndexError("index out of bounds in unpack")
+    if device_mode:
+        return _as_user_tensor(out).reshape(tuple(group_idx.shape))
+    return _download(out).reshape(np.shape(group_idx))
+
+
+# ------------------------------------------------------------------------------------------------
+# test hook: host-only planning (no device), used by tests/test_semantics.py to compare dtype /
+# shape / exception decisions with the reference's recorded answers on a machine without a GPU.
+# ------------------------------------------------------------------------------------------------
+def _plan_only_for_tests(group_idx, a, func="sum", size=None, fill_value=0, order="C", dtype=None, axis=None, **kwargs):
+    def resolve_on_host(plan, c):
+        g = np.asanyarray(c.group_idx)
+        if g.size == 0:
+            raise ValueError("zero-size array to reduction operation maximum which has no identity")
+        if (g < 0).any():
+            raise ValueError("negative indices not supported")
+        if plan.form == "flat":
+            plan.flat_size = int(g.max()) + 1
+        elif plan.form == "axis":
+            sem.finish_axis_plan(plan, int(g.max()) + 1)
+        else:
+            sem.finish_multi_plan(plan, [int(v) + 1 for v in g.max(axis=1)])
+    return _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, dict(kwargs), resolve_on_host)

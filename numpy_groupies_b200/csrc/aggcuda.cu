@@ -1,0 +1,231 @@
+// aggcuda.cu -- extern "C" entry points of libaggcuda.so (see include/aggcuda.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+#include "agc_common.cuh"
+#include "agc_generic.cuh"
+#include "agc_fast.cuh"
+#include "agc_scan.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return code; }
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "CUDA error at %s: %s", where, cudaGetErrorString(e));
+  return -100;
+}
+#define AGC_CUDA_OK(where) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return cuda_fail(e_, where); } while (0)
+
+int g_sm_count = 0;
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct Layout { int64_t t0, t1, t2, b0, b1, extra, total; };
+// table carve-up shared by agc_workspace_bytes / agc_partials / agc_aggregate
+Layout reduce_layout(int64_t size) {
+  Layout L; int64_t s8 = align_up(size * 8, 256), s1 = align_up(size, 256);
+  L.t0 = 0; L.t1 = s8; L.t2 = 2 * s8; L.b0 = 3 * s8; L.b1 = 3 * s8 + s1; L.extra = 3 * s8 + 2 * s1;
+  L.total = L.extra;
+  return L;
+}
+agc::Tables tables_at(void* ws, const Layout& L) {
+  char* b = (char*)ws; agc::Tables t;
+  t.t0f = (double*)(b + L.t0); t.t0i = (long long*)(b + L.t0); t.t1 = (long long*)(b + L.t1);
+  t.t2 = (double*)(b + L.t2); t.b0 = (unsigned char*)(b + L.b0); t.b1 = (unsigned char*)(b + L.b1);
+  return t;
+}
+
+bool is_reduction(int op) { return op >= AGC_OP_SUM && op <= AGC_OP_ANYNAN; }
+bool is_two_pass(int op) { return op == AGC_OP_VAR || op == AGC_OP_ARGMAX || op == AGC_OP_ARGMIN; }
+
+int check_request(const agc_request_t* r) {
+  if (!r) return fail(-1, "null request");
+  if (r->op < 0 || r->op >= AGC_OP_COUNT) return fail(-2, "unknown op");
+  if (r->a_dtype < 0 || r->a_dtype >= AGC_DT_COUNT) return fail(-3, "bad a_dtype");
+  if (r->out_dtype < 0 || r->out_dtype >= AGC_DT_COUNT) return fail(-3, "bad out_dtype");
+  if (r->index.dtype < 0 || r->index.dtype > AGC_DT_U64) return fail(-3, "labels must have an integer dtype");
+  if (r->n < 0 || r->size < 0) return fail(-4, "negative n or size");
+  if (r->index.form < 0 || r->index.form > AGC_FORM_MULTI) return fail(-5, "bad index form");
+  if (r->index.form != AGC_FORM_FLAT && (r->index.ndim < 1 || r->index.ndim > AGC_MAX_NDIM)) return fail(-5, "bad ndim");
+  if (r->n > 0 && !r->index.labels) return fail(-6, "null labels");
+  if (!r->status) return fail(-6, "null status");
+  if (!r->out && !(r->flags & AGC_F_ACC_ONLY) && (r->size > 0 || !is_reduction(r->op))) return fail(-6, "null out");
+  return 0;
+}
+
+int grid_for(int64_t work, int threads, int per_sm) {
+  int64_t blocks = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <class T>
+void launch_accumulate(const agc::AccParams& p, cudaStream_t st) {
+  if (p.n == 0) return;
+  agc::k_accumulate<T><<<grid_for(p.n, 256, 16), 256, 0, st>>>(p);
+}
+void launch_accumulate_cls(const agc::AccParams& p, cudaStream_t st) {
+  switch (p.a_dtype) {
+    case AGC_DT_F32: launch_accumulate<float>(p, st); break;
+    case AGC_DT_F64: launch_accumulate<double>(p, st); break;
+    case AGC_DT_U64: launch_accumulate<unsigned long long>(p, st); break;
+    default: launch_accumulate<long long>(p, st); break;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int agc_abi_version(void) { return AGC_ABI_VERSION; }
+const char* agc_last_error(void) { return g_err; }
+
+int64_t agc_workspace_bytes(const agc_request_t* r) {
+  if (check_request(r)) return -1;
+  if (is_reduction(r->op)) return reduce_layout(r->size).total + 256;
+  return agc::scan_workspace_bytes(r->op, r->n, r->size, r->a_dtype) + 256;
+}
+
+int agc_partials(const agc_request_t* r, agc_partial_t* out, int max_out) {
+  if (check_request(r)) return -1;
+  if (!is_reduction(r->op)) return fail(-7, "N->N operations have no mergeable partial tables");
+  Layout L = reduce_layout(r->size);
+  agc_partial_t tmp[5]; int k = 0;
+  const bool fl = agc::acc_is_float(r->op, r->a_dtype, r->out_dtype);
+  auto add = [&](int64_t off, int dt, int red) { tmp[k].offset_bytes = off; tmp[k].count = r->size; tmp[k].dtype = dt; tmp[k].reduce = red; ++k; };
+  const bool pass2 = r->flags & AGC_F_PASS2;
+  switch (r->op) {
+    case AGC_OP_SUM: case AGC_OP_SUMSQ: add(L.t0, fl ? AGC_DT_F64 : AGC_DT_I64, 0); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_PROD: add(L.t0, fl ? AGC_DT_F64 : AGC_DT_I64, 3); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_LEN: add(L.t1, AGC_DT_I64, 0); break;
+    case AGC_OP_MEAN: add(L.t0, AGC_DT_F64, 0); add(L.t1, AGC_DT_I64, 0); break;
+    case AGC_OP_VAR: if (pass2) add(L.t2, AGC_DT_F64, 0); else { add(L.t0, AGC_DT_F64, 0); add(L.t1, AGC_DT_I64, 0); } break;
+    case AGC_OP_MAX: add(L.t0, AGC_DT_I64, 1); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_MIN: add(L.t0, AGC_DT_I64, 2); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_ARGMAX: if (pass2) add(L.t1, AGC_DT_I64, 2); else add(L.t0, AGC_DT_I64, 1); break;
+    case AGC_OP_ARGMIN: if (pass2) add(L.t1, AGC_DT_I64, 2); else add(L.t0, AGC_DT_I64, 2); break;
+    case AGC_OP_ANY: case AGC_OP_ANYNAN: add(L.b0, AGC_DT_U8, 1); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_ALL: case AGC_OP_ALLNAN: add(L.b0, AGC_DT_U8, 2); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_FIRST: add(L.t1, AGC_DT_I64, 2); break;
+    case AGC_OP_LAST: add(L.t1, AGC_DT_I64, 1); break;
+    default: break;
+  }
+  for (int i = 0; i < k && i < max_out; ++i) out[i] = tmp[i];
+  return k;
+}
+
+int agc_aggregate(const agc_request_t* r, void* stream) {
+  int rc = check_request(r);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!is_reduction(r->op)) {
+    rc = agc::run_scan_op(r, st, sm_count());
+    if (rc) return fail(rc, agc::scan_error());
+    AGC_CUDA_OK("N->N op");
+    return 0;
+  }
+  if (r->workspace_bytes < reduce_layout(r->size).total) return fail(-8, "workspace too small");
+  if (!r->workspace && r->size > 0) return fail(-6, "null workspace");
+  const Layout L = reduce_layout(r->size);
+  agc::Tables t = tables_at(r->workspace, L);
+  const bool acc = !(r->flags & AGC_F_FIN_ONLY), fin = !(r->flags & AGC_F_ACC_ONLY);
+  const bool pass2_only = (r->flags & AGC_F_PASS2) != 0;
+
+  agc::AccParams p;
+  memset(&p, 0, sizeof(p));
+  p.op = r->op; p.flags = r->flags; p.a_dtype = r->a_dtype; p.out_dtype = r->out_dtype; p.pass = 1;
+  p.a = r->a; p.a_sf = r->a_scalar_f64; p.a_si = r->a_scalar_i64;
+  p.ix.ix = r->index; p.ix.size = r->size; p.ix.n = r->n;
+  p.n = r->n; p.size = r->size; p.index_base = r->index_base; p.t = t; p.status = r->status;
+
+  if (acc) {
+    bool done = false;
+    if (!pass2_only) {
+      if (!(r->flags & AGC_F_NO_FAST) && !(r->flags & AGC_F_NO_INIT) && r->size > 0 && r->n > 0) {
+        // specialised shared-memory kernels (they initialise + write the same global tables)
+        int frc = agc::try_fast_path(r, t, st, sm_count());
+        if (frc < 0) return fail(frc, "fast path launch failed");
+        done = frc > 0;
+        AGC_CUDA_OK("fast path");
+      }
+      if (!done) {
+        if (!(r->flags & AGC_F_NO_INIT) && r->size > 0) {
+          agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
+          AGC_CUDA_OK("init");
+        }
+        launch_accumulate_cls(p, st);
+        AGC_CUDA_OK("accumulate");
+      }
+    }
+    if (is_two_pass(r->op) && (pass2_only || fin)) {
+      if (r->size > 0) {
+        if (r->op == AGC_OP_VAR) {
+          agc::k_means_inplace<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size);
+          if (pass2_only) agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 1);
+        } else if (pass2_only) {
+          agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 1);
+        }
+      }
+      p.pass = 2;
+      launch_accumulate_cls(p, st);
+      AGC_CUDA_OK("second pass");
+    }
+  }
+  if (fin && r->size > 0) {
+    agc::FinParams f;
+    memset(&f, 0, sizeof(f));
+    f.op = r->op; f.flags = r->flags; f.a_dtype = r->a_dtype; f.out_dtype = r->out_dtype; f.a = r->a; f.out = r->out;
+    f.fill_f = r->fill_f64; f.fill_i = r->fill_i64; f.ddof = r->ddof; f.size = r->size; f.index_base = r->index_base;
+    f.arg_stride = r->arg_stride; f.arg_len = r->arg_len; f.n = r->n; f.t = t;
+    agc::k_finalize<<<grid_for(r->size, 256, 8), 256, 0, st>>>(f);
+    AGC_CUDA_OK("finalize");
+  }
+  return 0;
+}
+
+int agc_label_minmax(const void* labels, int32_t dtype, int64_t n, int64_t* out_minmax, void* stream) {
+  if (n <= 0 || !labels || !out_minmax) return fail(-6, "agc_label_minmax: empty or null input");
+  if (dtype < 0 || dtype > AGC_DT_U64) return fail(-3, "labels must have an integer dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  agc::k_minmax_init<<<1, 1, 0, st>>>((long long*)out_minmax);
+  agc::k_label_minmax<<<grid_for(n, 256, 8), 256, 0, st>>>(labels, dtype, n, (long long*)out_minmax);
+  AGC_CUDA_OK("label_minmax");
+  return 0;
+}
+
+int agc_unpack(const void* table, int32_t elem_bytes, int64_t size, const void* labels, int32_t dtype, int64_t n,
+               void* out, int32_t* status, void* stream) {
+  if (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8) return fail(-3, "elem_bytes must be 1/2/4/8");
+  if (n == 0) return 0;
+  if (!table || !labels || !out || !status) return fail(-6, "agc_unpack: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  agc::k_unpack<<<grid_for(n, 256, 16), 256, 0, st>>>(table, elem_bytes, size, labels, dtype, n, out, status);
+  AGC_CUDA_OK("unpack");
+  return 0;
+}
+
+int64_t agc_group_order_workspace_bytes(int64_t n, int64_t size) { return agc::sort_workspace_bytes(n, size) + 256; }
+
+int agc_group_order(const agc_index_t* index, int64_t n, int64_t size, int64_t* order, int64_t* offsets,
+                    void* workspace, int64_t workspace_bytes, int32_t* status, void* stream) {
+  if (!index || !order || !status) return fail(-6, "agc_group_order: null pointer");
+  if (workspace_bytes < agc::sort_workspace_bytes(n, size)) return fail(-8, "workspace too small");
+  int rc = agc::group_order(*index, n, size, (long long*)order, (long long*)offsets, workspace, status, (cudaStream_t)stream, sm_count());
+  if (rc) return fail(rc, agc::scan_error());
+  AGC_CUDA_OK("group_order");
+  return 0;
+}
+
+}  // extern "C"
