@@ -148,6 +148,13 @@ int64_t     agc_group_order_workspace_bytes(int64_t n, int64_t size);
 int         agc_group_order(const agc_index_t* index, int64_t n, int64_t size, int64_t* order, int64_t* offsets,
                             void* workspace, int64_t workspace_bytes, int32_t* status, void* stream);
 
+/* measurement hooks (bench.py): when enabled, agc_aggregate brackets its dominant accumulate kernel with
+ * CUDA events on the caller's stream; agc_profile_last_ms() waits for that kernel and returns its duration.
+ * agc_launch_count() = number of libaggcuda kernels launched by this process so far. */
+int         agc_profile_enable(int on);
+float       agc_profile_last_ms(void);
+int64_t     agc_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

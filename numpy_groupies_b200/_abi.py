@@ -44,7 +44,8 @@ class Partial(C.Structure):
 
 
 EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_partials", "agc_aggregate",
-           "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order")
+           "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order",
+           "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count")
 
 _lib = None
 
@@ -80,6 +81,10 @@ def load():
     lib.agc_group_order.restype = C.c_int
     lib.agc_group_order.argtypes = [C.POINTER(Index), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_void_p]
+    lib.agc_profile_enable.restype = C.c_int
+    lib.agc_profile_enable.argtypes = [C.c_int]
+    lib.agc_profile_last_ms.restype = C.c_float
+    lib.agc_launch_count.restype = C.c_int64
     if lib.agc_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libaggcuda ABI {lib.agc_abi_version()} != expected {ABI_VERSION}: rebuild")
     _lib = lib

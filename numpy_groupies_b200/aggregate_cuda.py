@@ -157,8 +157,20 @@ def _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, kwargs, r
 
     # --- what kind of inputs ------------------------------------------------------------------
     c.device_mode = _is_tensor(group_idx) or _is_tensor(a)
+    c.return_cpu = False
     if c.device_mode:
         torch = _t()
+        cpu_in = [x for x in (group_idx, a) if _is_tensor(x) and not x.is_cuda]
+        if cpu_in:                                          # host torch tensors (e.g. pinned): H2D here, result goes back
+            if any(_is_tensor(x) and x.is_cuda for x in (group_idx, a)):
+                raise ValueError("group_idx and a must live on the same device")
+            _require_cuda()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            if _is_tensor(group_idx):
+                group_idx = group_idx.to(dev, non_blocking=True)
+            if _is_tensor(a):
+                a = a.to(dev, non_blocking=True)
+            c.return_cpu = True
         if not _is_tensor(group_idx):
             group_idx = torch.as_tensor(np.asanyarray(group_idx), device=a.device)
         g_shape, g_dtype = tuple(group_idx.shape), _tensor_np_dtype(group_idx)
@@ -528,7 +540,8 @@ def aggregate(group_idx, a, func="sum", size=None, fill_value=0, order="C", dtyp
     if c.kind == "device":
         out = _run_device(c)
         if c.device_mode:
-            return _finish_shape_torch(c, _as_user_tensor(out))
+            res = _finish_shape_torch(c, _as_user_tensor(out))
+            return res.cpu() if c.return_cpu else res
         return _finish_shape_np(c, _download(out))
     if c.kind == "array":
         ret = _run_array(c)

@@ -16,6 +16,10 @@
 
 namespace agc {
 
+// kernels launched by this library so far (bench.py reports it as `gpu_launches`)
+static long long g_launches = 0;
+#define AGC_COUNT_LAUNCH(n_) (::agc::g_launches += (n_))
+
 // ---------------------------------------------------------------------------------------------
 // value classes: every input dtype is widened at load time to one of four classes
 // ---------------------------------------------------------------------------------------------

@@ -1,7 +1,244 @@
-// agc_fast.cuh -- specialised shared-memory kernels (placeholder until the first GPU parity run).
+// agc_fast.cuh -- shared-memory-privatised scatter-reduce for the headline Form-1 workloads
+// (f32 values, int64/int32 labels; sum / sumofsquares / mean / min / max / len and nan-variants).
+//
+// Design, from the measurements in ubench/ (profiles/r01_probe*.md):
+//   * the only shared-memory atomics that are native on sm_100a are 32-bit INTEGER ops
+//     (ATOMS.ADD / ATOMS.MIN / ATOMS.MAX); float atomicAdd in shared memory is a CAS loop that
+//     collapses under skew, global RED collapses on hot addresses.  Native ATOMS at 2048
+//     threads/SM sustain ~500 Gelem/s (>90 % of the HBM roofline) for uniform AND Zipf labels.
+//   * so every accumulator is an integer:
+//       sum   -> 64-bit FIXED POINT (two u32 words, carry propagated with a second ATOMS) whose
+//                scale is chosen per CTA from the data: a value whose exponent lies in the
+//                16-binade window below the CTA's reference exponent converts EXACTLY
+//                (24-bit mantissa << 1..16); anything else (huge, tiny, inf, NaN) bypasses to the
+//                global f64 table with one RED.  The result is therefore at least as accurate
+//                as the reference's sequential f64 sum, and independent of the order of
+//                elements inside a CTA.
+//       count -> u32 word;   min/max -> order-preserving s32 key of the f32 bits.
+//   * each CTA owns a private table in shared memory (size*words*4 B), streams its share of
+//     (labels, a) with 128-bit L1-bypassing loads, and finally merges the table into the global
+//     accumulator tables of agc_generic.cuh with one RED per touched group.
 #pragma once
 #include "agc_generic.cuh"
+
 namespace agc {
-// returns 1 if it handled accumulation into the global tables, 0 to fall back, <0 on error
-inline int try_fast_path(const agc_request_t*, const Tables&, cudaStream_t, int) { return 0; }
+
+enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4 };
+
+constexpr int FX_F = 40;          // fixed-point fraction bits below the reference exponent
+constexpr int FX_WINDOW = 16;     // binades that convert exactly: FX_F - 24
+constexpr int FAST_THREADS = 1024;
+constexpr long long FAST_MAX_PER_CTA = 1ll << 22;   // keeps 64-bit fixed point and u32 counts from overflowing
+
+struct FastParams {
+  const void* labels; const float* a;
+  long long n, size;
+  Tables t;
+  int* status;
+  int flags;            // AGC_F_NANSKIP, AGC_F_NEED_TOUCHED
+  int square;           // sumofsquares: accumulate (float)(v*v)
+  int want_b1;          // write touched flags (sum with fill != 0)
+  int want_cnt;         // merge counts into T1 (mean / var)
+};
+
+__device__ __forceinline__ void fx_add(unsigned* lo, unsigned* hi, long long q) {
+  unsigned ql = (unsigned)q; int qh = (int)(q >> 32);
+  unsigned old = atomicAdd(lo, ql);
+  qh += (old + ql < old);                       // carry out of the low word
+  if (qh != 0) atomicAdd(hi, (unsigned)qh);
+}
+
+template <class LT> struct LabelVec;
+template <> struct LabelVec<long long> {
+  // 4 consecutive int64 labels = two 16-byte loads
+  static __device__ __forceinline__ void load(const void* base, long long v, long long (&g)[4]) {
+    int4 l0 = ldg_stream16((const int4*)base + 2 * v), l1 = ldg_stream16((const int4*)base + 2 * v + 1);
+    g[0] = ((long long)(unsigned)l0.x) | ((long long)l0.y << 32); g[1] = ((long long)(unsigned)l0.z) | ((long long)l0.w << 32);
+    g[2] = ((long long)(unsigned)l1.x) | ((long long)l1.y << 32); g[3] = ((long long)(unsigned)l1.z) | ((long long)l1.w << 32);
+  }
+  static __device__ __forceinline__ long long one(const void* base, long long i) { return ((const long long*)base)[i]; }
+};
+template <> struct LabelVec<int> {
+  static __device__ __forceinline__ void load(const void* base, long long v, long long (&g)[4]) {
+    int4 l = ldg_stream16((const int4*)base + v);
+    g[0] = l.x; g[1] = l.y; g[2] = l.z; g[3] = l.w;
+  }
+  static __device__ __forceinline__ long long one(const void* base, long long i) { return ((const int*)base)[i]; }
+};
+
+template <int MODE, class LT, bool LOAD_A>
+__global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
+  extern __shared__ unsigned sw[];
+  __shared__ unsigned s_maxbits;
+  constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
+  const int G = (int)p.size;
+  unsigned* w0 = sw;            // sum.lo | key | count(FM_LEN)
+  unsigned* w1 = sw + G;        // sum.hi
+  unsigned* w2 = sw + 2 * G;    // count (FM_SUMCNT)
+  const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
+  for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;
+  if (threadIdx.x == 0) s_maxbits = 0u;
+  __syncthreads();
+
+  const long long nvec = p.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  bool bad = false;
+
+  // ---- reference exponent of this CTA: from its first tile ---------------------------------------
+  unsigned lo_bits = 0, span_bits = 0; double scale = 1.0, inv_scale = 1.0;
+  if (MODE == FM_SUM || MODE == FM_SUMCNT) {
+    unsigned m = 0;
+    if (v < nvec) {
+      int4 av = ldg_stream16((const int4*)p.a + v);
+      unsigned b[4] = {(unsigned)av.x & 0x7fffffffu, (unsigned)av.y & 0x7fffffffu, (unsigned)av.z & 0x7fffffffu, (unsigned)av.w & 0x7fffffffu};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned bb = b[k];
+        if (p.square) { float f = __uint_as_float(bb); bb = __float_as_uint(f * f); }
+        if (bb < 0x7f800000u && bb > m) m = bb;
+      }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_maxbits, m);
+    __syncthreads();
+    int eb = (int)(s_maxbits >> 23);            // biased exponent of the largest finite |value| seen
+    if (eb == 0) eb = 127;                      // tile was all zero / non-finite: assume O(1) data
+    eb += 1;                                    // values with biased exponent < eb convert
+    int lo_e = eb - FX_WINDOW; if (lo_e < 1) lo_e = 1;
+    lo_bits = (unsigned)lo_e << 23;
+    span_bits = (unsigned)(eb - lo_e) << 23;
+    // q = v * 2^(FX_F - (eb-127)) ; exact for in-window values
+    scale = __longlong_as_double((long long)(1023 + FX_F - (eb - 127)) << 52);
+    inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
+  }
+
+  auto update = [&](long long g, float x) {
+    if (g < 0 || g >= p.size) { bad = true; return; }
+    const int gi = (int)g;
+    if (MODE == FM_LEN) {
+      if (LOAD_A && nanskip && x != x) return;
+      atomicAdd(w0 + gi, 1u);
+    } else if (MODE == FM_MAX || MODE == FM_MIN) {
+      int k;
+      if (x != x) { if (nanskip) return; k = MODE == FM_MAX ? 0x7fffffff : (int)0x80000000; }   // NaN wins
+      else k = key32_of(x);
+      if (MODE == FM_MAX) atomicMax((int*)w0 + gi, k); else atomicMin((int*)w0 + gi, k);
+    } else {
+      if (nanskip && x != x) return;
+      if (p.square) x = x * x;
+      unsigned ab = __float_as_uint(x) & 0x7fffffffu;
+      if (ab - lo_bits < span_bits) {
+        long long q = __double2ll_rn((double)x * scale);
+        fx_add(w0 + gi, w1 + gi, q);
+      } else if (ab != 0u) {
+        atomicAdd(p.t.t0f + g, (double)x);          // out of window (huge / tiny / inf / NaN): exact f64 RED
+      }
+      if (MODE == FM_SUMCNT) atomicAdd(w2 + gi, 1u);
+    }
+  };
+
+  for (; v < nvec; v += stride) {
+    long long g[4];
+    LabelVec<LT>::load(p.labels, v, g);
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (LOAD_A) {
+      int4 av = ldg_stream16((const int4*)p.a + v);
+      x[0] = __int_as_float(av.x); x[1] = __int_as_float(av.y); x[2] = __int_as_float(av.z); x[3] = __int_as_float(av.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) update(g[k], x[k]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {          // tail elements
+    long long i = (nvec << 2) + threadIdx.x;
+    update(LabelVec<LT>::one(p.labels, i), LOAD_A ? p.a[i] : 0.f);
+  }
+  if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = 10 + MODE;
+  __syncthreads();
+
+  // ---- merge the CTA's table into the global accumulator tables -----------------------------------
+  for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
+    if (MODE == FM_LEN) {
+      unsigned c = w0[gi];
+      if (c) atomicAdd((unsigned long long*)(p.t.t1 + gi), (unsigned long long)c);
+    } else if (MODE == FM_MAX || MODE == FM_MIN) {
+      int k = (int)w0[gi];
+      if (k != (int)init0) {
+        long long k64;
+        if (MODE == FM_MAX) k64 = k == 0x7fffffff ? AGC_EMPTY_MIN : key_of((double)unkey_f32(k));
+        else k64 = k == (int)0x80000000 ? AGC_EMPTY_MAX : key_of((double)unkey_f32(k));
+        if (MODE == FM_MAX) atomicMax(p.t.t0i + gi, k64); else atomicMin(p.t.t0i + gi, k64);
+      }
+    } else {
+      long long q = (long long)(((unsigned long long)w1[gi] << 32) | w0[gi]);
+      if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
+      if (MODE == FM_SUMCNT) {
+        unsigned c = w2[gi];
+        if (c) {
+          if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + gi), (unsigned long long)c);
+          if (p.want_b1) p.t.b1[gi] = 1;
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, class LT, bool LOAD_A>
+inline int launch_fast(const FastParams& p, int ctas_per_sm, size_t smem, cudaStream_t st, int sms) {
+  auto kern = k_fast<MODE, LT, LOAD_A>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
+    attr_done = true;
+  }
+  AGC_COUNT_LAUNCH(1), kern<<<sms * ctas_per_sm, FAST_THREADS, smem, st>>>(p);
+  return 1;
+}
+
+// returns 1 if it accumulated into the global tables (which it also initialises), 0 to fall back
+inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
+  if (r->index.form != AGC_FORM_FLAT) return 0;
+  if (r->index.dtype != AGC_DT_I64 && r->index.dtype != AGC_DT_I32) return 0;
+  const int op = r->op;
+  const bool is_len = op == AGC_OP_LEN;
+  const bool nanskip = r->flags & AGC_F_NANSKIP;
+  if (!(op == AGC_OP_SUM || op == AGC_OP_SUMSQ || op == AGC_OP_MEAN || op == AGC_OP_MIN || op == AGC_OP_MAX || is_len || op == AGC_OP_VAR))
+    return 0;
+  const bool need_a = !is_len || nanskip;
+  if (need_a && (r->a == nullptr || r->a_dtype != AGC_DT_F32)) return 0;
+  if (r->n < (1 << 16) || r->size > (1 << 16)) return 0;
+  if (((uintptr_t)r->index.labels & 15) || (need_a && ((uintptr_t)r->a & 15))) return 0;
+  int mode;
+  const bool want_b1 = (op == AGC_OP_SUM || op == AGC_OP_SUMSQ) && (r->flags & AGC_F_NEED_TOUCHED);
+  if (is_len) mode = FM_LEN;
+  else if (op == AGC_OP_MAX) mode = FM_MAX;
+  else if (op == AGC_OP_MIN) mode = FM_MIN;
+  else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
+  else mode = FM_SUM;
+  const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
+  const size_t smem = (size_t)r->size * words * 4;
+  const size_t cap2 = 110 * 1024, cap1 = 227 * 1024 - 1024;
+  if (smem > cap1) return 0;
+  const int ctas = smem <= cap2 ? 2 : 1;
+  if (r->n > (long long)sms * ctas * FAST_MAX_PER_CTA) return 0;
+
+  FastParams p;
+  p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
+  p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
+  p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
+  AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
+  const bool i64 = r->index.dtype == AGC_DT_I64;
+  int rc = 0;
+#define AGC_FAST_CASE(M)                                                                          \
+  if (mode == M) {                                                                                \
+    if (i64) rc = need_a ? launch_fast<M, long long, true>(p, ctas, smem, st, sms) : launch_fast<M, long long, false>(p, ctas, smem, st, sms); \
+    else     rc = need_a ? launch_fast<M, int, true>(p, ctas, smem, st, sms) : launch_fast<M, int, false>(p, ctas, smem, st, sms);             \
+  }
+  AGC_FAST_CASE(FM_SUM) AGC_FAST_CASE(FM_SUMCNT) AGC_FAST_CASE(FM_MAX) AGC_FAST_CASE(FM_MIN) AGC_FAST_CASE(FM_LEN)
+#undef AGC_FAST_CASE
+  return rc;
+}
+
 }  // namespace agc

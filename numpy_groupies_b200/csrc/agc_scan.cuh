@@ -1,8 +1,19 @@
-// agc_scan.cuh -- label utilities (min/max, unpack) and the N->N family (scans, sort).
+// agc_scan.cuh -- label utilities (min/max, unpack) and the N->N family:
+//   * stable LSD radix sort-by-key (8-bit digits; keys = flat group or value key, payload = position)
+//   * segmented inclusive scans over (sorted key, value) for cumsum / cumprod / cummax / cummin
+//   * func='sort' (values ordered inside each group, written back to the group's own slots)
+//   * group order + CSR offsets for func='array' and generic callables
+// Reference semantics: aggregate_numpy.py:210-266 and aggregate_numba.py:218-225,487-500.
+// Sortedness of the flat labels is detected on the device; already-sorted labels skip every sort
+// pass without a host round trip (the sort kernels read the flag and return).
 #pragma once
 #include "agc_generic.cuh"
+
 namespace agc {
 
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
 __global__ void k_minmax_init(long long* mm) { mm[0] = 0x7fffffffffffffffll; mm[1] = (long long)0x8000000000000000ll; }
 
 __global__ void k_label_minmax(const void* labels, int dtype, long long n, long long* mm) {
@@ -37,10 +48,530 @@ __global__ void k_unpack(const void* table, int eb, long long size, const void* 
   if (bad) status[AGC_ST_BADLABEL] = 1;
 }
 
-inline const char* scan_error() { return "N->N operations are not built yet"; }
-inline int64_t scan_workspace_bytes(int, int64_t, int64_t, int) { return 0; }
-inline int64_t sort_workspace_bytes(int64_t, int64_t) { return 0; }
-inline int run_scan_op(const agc_request_t*, cudaStream_t, int) { return -20; }
-inline int group_order(const agc_index_t&, int64_t, int64_t, long long*, long long*, void*, int*, cudaStream_t, int) { return -20; }
+static thread_local const char* g_scan_err = "";
+inline const char* scan_error() { return g_scan_err; }
+
+// ---------------------------------------------------------------------------------------------
+// device-wide exclusive scan of u32 counters (3 kernels, in place)
+// ---------------------------------------------------------------------------------------------
+constexpr int XS_THREADS = 256, XS_ITEMS = 16, XS_TILE = XS_THREADS * XS_ITEMS;
+
+__device__ __forceinline__ unsigned block_exclusive_scan_u32(unsigned x, unsigned* total) {
+  __shared__ unsigned wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned inc = x;
+  for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned s = lane < nw ? wsum[lane] : 0, si = s;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+    wsum[lane] = si - s;
+    if (lane == 31) *total = si;
+  }
+  __syncthreads();
+  unsigned r = wsum[w] + inc - x;
+  __syncthreads();
+  return r;
+}
+__global__ void k_xs_reduce(const unsigned* v, long long n, unsigned* tile_sums) {
+  __shared__ unsigned tot;
+  long long base = (long long)blockIdx.x * XS_TILE + (long long)threadIdx.x * XS_ITEMS;
+  unsigned s = 0;
+  for (int k = 0; k < XS_ITEMS; ++k) if (base + k < n) s += v[base + k];
+  block_exclusive_scan_u32(s, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+__global__ void k_xs_scan_sums(unsigned* tile_sums, int ntiles) {      // single block, serial-in-thread chunks
+  __shared__ unsigned tot;
+  const int per = (ntiles + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per;
+  unsigned s = 0;
+  for (int k = 0; k < per; ++k) if (b + k < ntiles) s += tile_sums[b + k];
+  unsigned run = block_exclusive_scan_u32(s, &tot);
+  for (int k = 0; k < per; ++k) if (b + k < ntiles) { unsigned t = tile_sums[b + k]; tile_sums[b + k] = run; run += t; }
+}
+__global__ void k_xs_apply(unsigned* v, long long n, const unsigned* tile_sums) {
+  __shared__ unsigned tot;
+  long long base = (long long)blockIdx.x * XS_TILE + (long long)threadIdx.x * XS_ITEMS;
+  unsigned x[XS_ITEMS], s = 0;
+  for (int k = 0; k < XS_ITEMS; ++k) { x[k] = base + k < n ? v[base + k] : 0; s += x[k]; }
+  unsigned run = block_exclusive_scan_u32(s, &tot) + tile_sums[blockIdx.x];
+  for (int k = 0; k < XS_ITEMS; ++k) if (base + k < n) { v[base + k] = run; run += x[k]; }
+}
+inline long long xs_tiles(long long n) { return (n + XS_TILE - 1) / XS_TILE; }
+inline void exclusive_scan_u32(unsigned* v, long long n, unsigned* tile_sums, cudaStream_t st) {
+  int nt = (int)xs_tiles(n);
+  AGC_COUNT_LAUNCH(1), k_xs_reduce<<<nt, XS_THREADS, 0, st>>>(v, n, tile_sums);
+  AGC_COUNT_LAUNCH(1), k_xs_scan_sums<<<1, 1024, 0, st>>>(tile_sums, nt);
+  AGC_COUNT_LAUNCH(1), k_xs_apply<<<nt, XS_THREADS, 0, st>>>(v, n, tile_sums);
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix sort-by-key: one 8-bit pass = histogram -> scan -> stable scatter
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256, RS_CHUNKS = 32, RS_TILE = RS_THREADS * RS_CHUNKS;
+inline int rs_blocks(long long n) { return (int)((n + RS_TILE - 1) / RS_TILE); }
+
+template <class K>
+__global__ void k_radix_hist(const K* keys, long long n, int shift, unsigned* hist, int nblocks, const int* run_flag) {
+  if (run_flag && *run_flag == 0) return;
+  __shared__ unsigned h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RS_TILE;
+  for (int c = 0; c < RS_CHUNKS; ++c) {
+    long long i = base + c * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  hist[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+template <class K>
+__global__ void k_radix_scatter(const K* kin, const unsigned* vin, K* kout, unsigned* vout, long long n, int shift,
+                                const unsigned* offs, int nblocks, const int* run_flag) {
+  if (run_flag && *run_flag == 0) return;
+  __shared__ unsigned running[256];
+  __shared__ unsigned warp_cnt[RS_THREADS / 32][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  running[threadIdx.x] = offs[(long long)threadIdx.x * nblocks + blockIdx.x];
+  for (int k = 0; k < RS_THREADS / 32; ++k) warp_cnt[k][threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RS_TILE;
+  for (int c = 0; c < RS_CHUNKS; ++c) {
+    long long i = base + c * RS_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    K key = valid ? kin[i] : K(0);
+    unsigned val = valid ? vin[i] : 0u;
+    unsigned d = valid ? ((unsigned)(key >> shift) & 0xffu) : (256u + lane);
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) warp_cnt[w][d] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      unsigned off = running[d] + rank;
+      for (int k = 0; k < w; ++k) off += warp_cnt[k][d];
+      kout[off] = key; vout[off] = val;
+    }
+    __syncthreads();
+    unsigned add = 0;
+    for (int k = 0; k < RS_THREADS / 32; ++k) { add += warp_cnt[k][threadIdx.x]; warp_cnt[k][threadIdx.x] = 0; }
+    running[threadIdx.x] += add;
+    __syncthreads();
+  }
+}
+
+struct SortBufs {
+  void* k[2]; unsigned* v[2]; unsigned* hist; unsigned* tile_sums;
+};
+// sorts bits [lo_bit, hi_bit) ; returns which buffer (0/1) holds the result. run_flag (device int, may be
+// NULL) == 0 turns every kernel into a no-op, in which case the data stays in buffer `src`.
+template <class K>
+inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int hi_bit, const int* run_flag, cudaStream_t st) {
+  if (n == 0) return src;
+  const int nb = rs_blocks(n);
+  for (int shift = lo_bit; shift < hi_bit; shift += 8) {
+    AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<nb, RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, run_flag);
+    exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st);
+    AGC_COUNT_LAUNCH(1), k_radix_scatter<K><<<nb, RS_THREADS, 0, st>>>((const K*)b.k[src], b.v[src], (K*)b.k[src ^ 1], b.v[src ^ 1], n, shift,
+                                                   b.hist, nb, run_flag);
+    src ^= 1;
+  }
+  return src;
+}
+
+// ---------------------------------------------------------------------------------------------
+// key generation: flat group of every element (+ sortedness + bad-label detection)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_group_keys(Indexer ix, long long n, unsigned* keys, unsigned* pos, int* status, int* unsorted) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  bool bad = false, uns = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long g = ix.group(i);
+    if (g < 0) { bad = true; g = 0; }
+    keys[i] = (unsigned)g; pos[i] = (unsigned)i;
+    if (i > 0) { long long gp = ix.group(i - 1); if (gp > g) uns = true; }
+  }
+  if (bad) status[AGC_ST_BADLABEL] = 1;
+  if (uns) *unsorted = 1;
+}
+__global__ void k_zero_int(int* p) { *p = 0; }
+__global__ void k_report_unsorted(const int* unsorted, int* status) { if (*unsorted) status[AGC_ST_UNSORTED] = 1; }
+
+// ---------------------------------------------------------------------------------------------
+// segmented scans
+// ---------------------------------------------------------------------------------------------
+enum { SC_SUM = 0, SC_PROD = 1, SC_MAX = 2, SC_MIN = 3 };
+constexpr int SG_THREADS = 256, SG_ITEMS = 8, SG_TILE = SG_THREADS * SG_ITEMS;
+
+template <class A, int OP> struct ScanOp;
+template <class A> struct ScanOp<A, SC_SUM> { static __device__ __forceinline__ A apply(A x, A y) { return x + y; } };
+template <> struct ScanOp<long long, SC_SUM> {
+  static __device__ __forceinline__ long long apply(long long x, long long y) { return (long long)((unsigned long long)x + (unsigned long long)y); } };
+template <class A> struct ScanOp<A, SC_PROD> { static __device__ __forceinline__ A apply(A x, A y) { return x * y; } };
+template <> struct ScanOp<long long, SC_PROD> {
+  static __device__ __forceinline__ long long apply(long long x, long long y) { return (long long)((unsigned long long)x * (unsigned long long)y); } };
+template <class A> struct ScanOp<A, SC_MAX> { static __device__ __forceinline__ A apply(A x, A y) { return x > y ? x : y; } };
+template <class A> struct ScanOp<A, SC_MIN> { static __device__ __forceinline__ A apply(A x, A y) { return x < y ? x : y; } };
+
+struct ScanParams {
+  const unsigned* keys[2]; const unsigned* pos[2];    // [0] = as generated (sorted input), [1] = after the sort
+  const int* unsorted;                                // selects between them on the device
+  const void* a; int a_dtype; int out_dtype; void* out;
+  long long n; int flags;
+  double fill_f; long long fill_i;
+  int a_float;                                        // value class of a
+  int a_u64;
+};
+
+// element k of the sorted sequence -> the value fed to the scan (A = double for float sum/prod,
+// long long otherwise; max/min always scan order-preserving integer keys)
+template <class A, int OP>
+__device__ __forceinline__ A scan_input(const ScanParams& p, unsigned src_pos, bool head) {
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  if (OP == SC_SUM || OP == SC_PROD) {
+    if (std::is_same<A, double>::value) {
+      double v;
+      if (p.a_dtype == AGC_DT_F32) v = ((const float*)p.a)[src_pos];
+      else if (p.a_dtype == AGC_DT_F64) v = ((const double*)p.a)[src_pos];
+      else if (p.a_u64) v = (double)((const unsigned long long*)p.a)[src_pos];
+      else v = (double)load_int(p.a, p.a_dtype, src_pos);
+      if (nanskip && v != v) v = OP == SC_SUM ? 0.0 : 1.0;
+      return (A)v;
+    } else {
+      return (A)load_int(p.a, p.a_dtype, src_pos);
+    }
+  } else {
+    const long long ident = OP == SC_MAX ? AGC_EMPTY_MAX : AGC_EMPTY_MIN;
+    const long long absorb = OP == SC_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX;
+    if (p.a_float) {
+      double v = p.a_dtype == AGC_DT_F32 ? (double)((const float*)p.a)[src_pos] : ((const double*)p.a)[src_pos];
+      if (v != v) return (A)((nanskip || !head) ? ident : absorb);   // numba: a NaN only sticks when it opens the group
+      return (A)key_of(v);
+    }
+    long long v = load_int(p.a, p.a_dtype, src_pos);
+    return (A)(p.a_u64 ? key_of((unsigned long long)v) : v);
+  }
+}
+template <class A, int OP>
+__device__ __forceinline__ void scan_store(const ScanParams& p, long long dst, A r) {
+  if (OP == SC_SUM || OP == SC_PROD) {
+    if (std::is_same<A, double>::value) store_from_f64(p.out, p.out_dtype, dst, (double)r);
+    else store_from_i64(p.out, p.out_dtype, dst, (long long)r, p.a_u64);
+  } else {
+    const long long ident = OP == SC_MAX ? AGC_EMPTY_MAX : AGC_EMPTY_MIN;
+    const long long absorb = OP == SC_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX;
+    long long k = (long long)r;
+    if (p.a_float) {
+      if (k == ident) { if (dtype_is_float(p.out_dtype)) store_from_f64(p.out, p.out_dtype, dst, p.fill_f); else store_from_i64(p.out, p.out_dtype, dst, p.fill_i); }
+      else store_from_f64(p.out, p.out_dtype, dst, k == absorb ? __longlong_as_double(0x7ff8000000000000ll) : unkey_f64(k));
+    } else {
+      store_from_i64(p.out, p.out_dtype, dst, p.a_u64 ? (long long)((unsigned long long)k ^ 0x8000000000000000ull) : k, p.a_u64);
+    }
+  }
+}
+
+// block-wide segmented inclusive scan of per-thread aggregates (flag, value); returns the EXCLUSIVE
+// prefix of this thread (has_prefix=false when nothing precedes it in the tile) and the tile aggregate.
+template <class A, int OP>
+__device__ __forceinline__ void block_seg_scan(bool f, A x, bool& pf, A& px, bool& have_p, bool& tile_f, A& tile_x) {
+  __shared__ unsigned char s_f[SG_THREADS / 32];
+  __shared__ long long s_x[SG_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  bool fi = f; A xi = x;                      // inclusive within warp
+  for (int o = 1; o < 32; o <<= 1) {
+    bool ft = __shfl_up_sync(0xffffffffu, (int)fi, o);
+    A xt = __shfl_up_sync(0xffffffffu, xi, o);
+    if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
+  }
+  if (lane == 31) { s_f[w] = fi; ((A*)s_x)[w] = xi; }
+  // exclusive within warp
+  bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); A xe = __shfl_up_sync(0xffffffffu, xi, 1);
+  __syncthreads();
+  // prefix over preceding warps (serial, <= 7 steps)
+  bool wf = false; A wx = A(0); bool have_w = false;
+  for (int k = 0; k < w; ++k) {
+    bool kf = s_f[k]; A kx = ((A*)s_x)[k];
+    if (!have_w) { wf = kf; wx = kx; have_w = true; }
+    else { if (!kf) wx = ScanOp<A, OP>::apply(wx, kx); else wx = kx; wf = wf | kf; }
+  }
+  // combine: prefix = warps-before (+) lanes-before-in-warp
+  if (lane == 0) { pf = wf; px = wx; have_p = have_w; }
+  else {
+    if (have_w && !fe) { px = ScanOp<A, OP>::apply(wx, xe); pf = wf | fe; }
+    else { px = xe; pf = fe | wf; }
+    have_p = true;
+  }
+  // tile aggregate = inclusive value of the last thread
+  {
+    bool tf = false; A tx = A(0); bool have = false;
+    for (int k = 0; k < SG_THREADS / 32; ++k) {
+      bool kf = s_f[k]; A kx = ((A*)s_x)[k];
+      if (!have) { tf = kf; tx = kx; have = true; }
+      else { if (!kf) tx = ScanOp<A, OP>::apply(tx, kx); else tx = kx; tf = tf | kf; }
+    }
+    tile_f = tf; tile_x = tx;
+  }
+  __syncthreads();
+}
+
+// PHASE 0: tile aggregates only.  PHASE 1: full scan with carry-in, writes the output.
+template <class A, int OP, int PHASE>
+__global__ void __launch_bounds__(SG_THREADS) k_seg_scan(const ScanParams p, unsigned char* tile_f, A* tile_x,
+                                                         const unsigned char* carry_ok, const A* carry_x) {
+  const int sel = *p.unsorted ? 1 : 0;
+  const unsigned* keys = p.keys[sel]; const unsigned* pos = p.pos[sel];
+  const long long base = (long long)blockIdx.x * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
+  A x[SG_ITEMS]; bool h[SG_ITEMS]; unsigned ps[SG_ITEMS];
+  unsigned prev = base > 0 && base - 1 < p.n ? keys[base - 1] : 0u;
+  bool tf = false; A tx = A(0); bool any = false;
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    long long i = base + k;
+    if (i < p.n) {
+      unsigned key = keys[i];
+      h[k] = (i == 0) || key != prev; prev = key;
+      ps[k] = pos[i];
+      x[k] = scan_input<A, OP>(p, ps[k], h[k]);
+      if (!any) { tf = h[k]; tx = x[k]; any = true; }
+      else { if (h[k]) tx = x[k]; else tx = ScanOp<A, OP>::apply(tx, x[k]); tf = tf | h[k]; }
+      x[k] = tx;                               // thread-local inclusive scan
+    } else { h[k] = true; ps[k] = 0; x[k] = A(0); }
+  }
+  if (!any) { tf = true; tx = A(0); }          // padding acts as a segment head: never merges
+  bool pf, have_p, agg_f; A px, agg_x;
+  block_seg_scan<A, OP>(tf, tx, pf, px, have_p, agg_f, agg_x);
+  if (PHASE == 0) {
+    if (threadIdx.x == 0) { tile_f[blockIdx.x] = agg_f; tile_x[blockIdx.x] = agg_x; }
+    return;
+  }
+  // carry from preceding tiles applies until the first head flag in this tile
+  bool have_c = blockIdx.x > 0 && carry_ok[blockIdx.x];
+  A cx = have_c ? carry_x[blockIdx.x] : A(0);
+  // full exclusive prefix for this thread = carry (+) in-tile prefix
+  bool have = false; A pre = A(0);
+  if (have_p) { pre = px; have = true; if (have_c && !pf) pre = ScanOp<A, OP>::apply(cx, px); }
+  else if (have_c) { pre = cx; have = true; }
+  bool open = have;                            // prefix still applies while no head has been seen in this thread
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    long long i = base + k;
+    if (i >= p.n) break;
+    if (h[k]) open = false;
+    A r = open ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
+    scan_store<A, OP>(p, (long long)ps[k], r);
+  }
+}
+
+// single block: inclusive segmented scan over tile aggregates -> carry for tile t = inclusive[t-1]
+template <class A, int OP>
+__global__ void k_seg_scan_tiles(const unsigned char* tile_f, const A* tile_x, int ntiles, unsigned char* carry_ok, A* carry_x) {
+  __shared__ unsigned char sf[1024];
+  __shared__ long long sx[1024];
+  const int per = (ntiles + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per;
+  bool f = false; A x = A(0); bool any = false;
+  for (int k = 0; k < per && b + k < ntiles; ++k) {
+    bool kf = tile_f[b + k]; A kx = tile_x[b + k];
+    if (!any) { f = kf; x = kx; any = true; } else { if (kf) x = kx; else x = ScanOp<A, OP>::apply(x, kx); f = f | kf; }
+  }
+  sf[threadIdx.x] = any ? f : 1; ((A*)sx)[threadIdx.x] = x;
+  __syncthreads();
+  // serial prefix over threads by thread 0..: 1024 entries, done cooperatively with a simple scan by one warp
+  if (threadIdx.x == 0) {
+    bool rf = false; A rx = A(0); bool have = false;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      bool kf = sf[t]; A kx = ((A*)sx)[t];
+      // store EXCLUSIVE prefix for thread t
+      sf[t] = have ? 1 : 0; A keep = rx;
+      if (!have) { rf = kf; rx = kx; have = true; } else { if (kf) rx = kx; else rx = ScanOp<A, OP>::apply(rx, kx); rf = rf | kf; }
+      ((A*)sx)[t] = keep;
+    }
+  }
+  __syncthreads();
+  bool have = sf[threadIdx.x]; A run = ((A*)sx)[threadIdx.x];
+  for (int k = 0; k < per && b + k < ntiles; ++k) {
+    carry_ok[b + k] = have; carry_x[b + k] = run;
+    bool kf = tile_f[b + k]; A kx = tile_x[b + k];
+    if (!have) { run = kx; have = true; } else { if (kf) run = kx; else run = ScanOp<A, OP>::apply(run, kx); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// func='sort' helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void k_value_keys(const void* a, int a_dtype, long long n, int reverse, unsigned long long* keys, unsigned* pos) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned long long u;
+    bool nan = false;
+    if (a_dtype == AGC_DT_F32) { float v = ((const float*)a)[i]; nan = v != v; u = (unsigned long long)key_of((double)v) ^ 0x8000000000000000ull; }
+    else if (a_dtype == AGC_DT_F64) { double v = ((const double*)a)[i]; nan = v != v; u = (unsigned long long)key_of(v) ^ 0x8000000000000000ull; }
+    else if (a_dtype == AGC_DT_U64) u = ((const unsigned long long*)a)[i];
+    else u = (unsigned long long)load_int(a, a_dtype, i) ^ 0x8000000000000000ull;
+    if (reverse) u = ~u;
+    if (nan) u = 0xffffffffffffffffull;                  // NaNs sort last in both directions (np.lexsort)
+    keys[i] = u; pos[i] = (unsigned)i;
+  }
+}
+__global__ void k_keys_of_positions(Indexer ix, long long n, const unsigned* pos, unsigned* keys) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long g = ix.group(pos[i]);
+    keys[i] = g < 0 ? 0u : (unsigned)g;
+  }
+}
+__global__ void k_sort_place(const void* a, int eb, long long n, const unsigned* slot_pos, const unsigned* src_pos, void* out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned d = slot_pos[i], s = src_pos[i];
+    switch (eb) {
+      case 1: ((unsigned char*)out)[d] = ((const unsigned char*)a)[s]; break;
+      case 2: ((unsigned short*)out)[d] = ((const unsigned short*)a)[s]; break;
+      case 4: ((unsigned*)out)[d] = ((const unsigned*)a)[s]; break;
+      default: ((unsigned long long*)out)[d] = ((const unsigned long long*)a)[s]; break;
+    }
+  }
+}
+__global__ void k_order_widen(const unsigned* p0, const unsigned* p1, const int* unsorted, long long n, long long* order) {
+  const unsigned* pos = *unsorted ? p1 : p0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) order[i] = pos[i];
+}
+__global__ void k_csr_offsets(const unsigned* keys0, const unsigned* keys1, const int* unsorted, long long n, long long size,
+                              long long* offsets) {
+  const unsigned* keys = *unsorted ? keys1 : keys0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g <= size; g += stride) {
+    long long lo = 0, hi = n;                               // lower_bound(keys, g)
+    while (lo < hi) { long long mid = (lo + hi) >> 1; if ((long long)keys[mid] < g) lo = mid + 1; else hi = mid; }
+    offsets[g] = lo;
+  }
+}
+__global__ void k_pos_select(const unsigned* p0, const unsigned* p1, const int* unsorted, long long n, unsigned* out) {
+  const unsigned* pos = *unsorted ? p1 : p0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) out[i] = pos[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------
+inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
+struct ScanWs {
+  int64_t k32[2], v[2], k64[2], v2[2], slot, hist, tsum, tile_f, tile_x, carry_f, carry_x, flag, total;
+};
+inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
+  ScanWs w; int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o += al256(bytes); return r; };
+  const int nb = rs_blocks(n > 0 ? n : 1);
+  w.k32[0] = take(n * 4); w.k32[1] = take(n * 4); w.v[0] = take(n * 4); w.v[1] = take(n * 4);
+  if (want_sort_op) { w.k64[0] = take(n * 8); w.k64[1] = take(n * 8); w.v2[0] = take(n * 4); w.v2[1] = take(n * 4); w.slot = take(n * 4); }
+  else { w.k64[0] = w.k64[1] = w.v2[0] = w.v2[1] = w.slot = 0; }
+  w.hist = take(256ll * nb * 4); w.tsum = take((xs_tiles(256ll * nb) + 1) * 4);
+  const long long ntiles = (n + SG_TILE - 1) / SG_TILE + 1;
+  w.tile_f = take(ntiles); w.tile_x = take(ntiles * 8); w.carry_f = take(ntiles); w.carry_x = take(ntiles * 8);
+  w.flag = take(256);
+  w.total = o;
+  return w;
+}
+inline int64_t scan_workspace_bytes(int op, int64_t n, int64_t, int) { return scan_ws_layout(n, op == AGC_OP_SORT).total; }
+inline int64_t sort_workspace_bytes(int64_t n, int64_t) { return scan_ws_layout(n, false).total; }
+
+inline int bits_for(long long size) { int b = 1; while (b < 32 && (1ll << b) < size) ++b; return (b + 7) / 8 * 8; }
+
+inline int scan_grid(long long n, int sms) { long long b = (n + 255) / 256; long long cap = (long long)sms * 16; return (int)(b < 1 ? 1 : (b > cap ? cap : b)); }
+
+// generate group keys, detect sortedness, sort (key, pos) by key unless sorted.  Leaves results addressed
+// through (keys[0|1], pos[0|1]) selected by *flag on the device.
+inline int group_sorted_pairs(const Indexer& ix, long long n, long long size, char* ws, const ScanWs& L, int* status,
+                              bool assume_sorted, cudaStream_t st, int sms, const unsigned* (&keys)[2], const unsigned* (&pos)[2],
+                              int*& flag) {
+  if (n >= (1ll << 32) || size > (1ll << 32)) { g_scan_err = "N->N / sort paths support n < 2^32 and size <= 2^32"; return -21; }
+  flag = (int*)(ws + L.flag);
+  AGC_COUNT_LAUNCH(1), k_zero_int<<<1, 1, 0, st>>>(flag);
+  unsigned* k0 = (unsigned*)(ws + L.k32[0]); unsigned* p0 = (unsigned*)(ws + L.v[0]);
+  if (n > 0) AGC_COUNT_LAUNCH(1), k_group_keys<<<scan_grid(n, sms), 256, 0, st>>>(ix, n, k0, p0, status, flag);
+  SortBufs b; b.k[0] = k0; b.k[1] = ws + L.k32[1]; b.v[0] = p0; b.v[1] = (unsigned*)(ws + L.v[1]);
+  b.hist = (unsigned*)(ws + L.hist); b.tile_sums = (unsigned*)(ws + L.tsum);
+  int res = 0;
+  if (!assume_sorted) res = radix_sort_pairs<unsigned>(b, 0, n, 0, bits_for(size), flag, st);
+  else AGC_COUNT_LAUNCH(1), k_report_unsorted<<<1, 1, 0, st>>>(flag, status);
+  keys[0] = k0; pos[0] = p0; keys[1] = (const unsigned*)b.k[res]; pos[1] = b.v[res];
+  return 0;
+}
+
+template <class A, int OP>
+inline void run_seg_scan(const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st) {
+  if (p.n == 0) return;
+  const int ntiles = (int)((p.n + SG_TILE - 1) / SG_TILE);
+  unsigned char* tf = (unsigned char*)(ws + L.tile_f); A* tx = (A*)(ws + L.tile_x);
+  unsigned char* cf = (unsigned char*)(ws + L.carry_f); A* cx = (A*)(ws + L.carry_x);
+  AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 0><<<ntiles, SG_THREADS, 0, st>>>(p, tf, tx, nullptr, nullptr);
+  AGC_COUNT_LAUNCH(1), k_seg_scan_tiles<A, OP><<<1, 1024, 0, st>>>(tf, tx, ntiles, cf, cx);
+  AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 1><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, nullptr, cf, cx);
+}
+
+inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
+  const long long n = r->n;
+  if (r->a == nullptr && n > 0) { g_scan_err = "N->N operations need an array a"; return -22; }
+  const bool sort_op = r->op == AGC_OP_SORT;
+  const ScanWs L = scan_ws_layout(n, sort_op);
+  if (r->workspace_bytes < L.total) { g_scan_err = "workspace too small"; return -8; }
+  char* ws = (char*)r->workspace;
+  Indexer ix; ix.ix = r->index; ix.size = r->size; ix.n = n;
+  const unsigned* keys[2]; const unsigned* pos[2]; int* flag = nullptr;
+  int rc = group_sorted_pairs(ix, n, r->size, ws, L, r->status, (r->flags & AGC_F_ASSUME_SORTED) != 0, st, sms, keys, pos, flag);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (sort_op) {
+    // slots: positions in group order
+    unsigned* slot = (unsigned*)(ws + L.slot);
+    AGC_COUNT_LAUNCH(1), k_pos_select<<<scan_grid(n, sms), 256, 0, st>>>(pos[0], pos[1], flag, n, slot);
+    // elements ordered by (group, value): sort by value key, then stably by group
+    SortBufs b; b.k[0] = ws + L.k64[0]; b.k[1] = ws + L.k64[1]; b.v[0] = (unsigned*)(ws + L.v2[0]); b.v[1] = (unsigned*)(ws + L.v2[1]);
+    b.hist = (unsigned*)(ws + L.hist); b.tile_sums = (unsigned*)(ws + L.tsum);
+    AGC_COUNT_LAUNCH(1), k_value_keys<<<scan_grid(n, sms), 256, 0, st>>>(r->a, r->a_dtype, n, (r->flags & AGC_F_REVERSE) ? 1 : 0,
+                                                    (unsigned long long*)b.k[0], b.v[0]);
+    int lo_bit = 0;
+    if (r->a_dtype == AGC_DT_F32) lo_bit = 24;              // f32 widened to f64: low 29 mantissa bits are zero
+    int res = radix_sort_pairs<unsigned long long>(b, 0, n, lo_bit, 64, nullptr, st);
+    // group keys of the value-ordered positions, then a stable sort by group
+    SortBufs g; g.k[0] = ws + L.k32[0]; g.k[1] = ws + L.k32[1]; g.v[0] = b.v[res]; g.v[1] = b.v[res ^ 1];
+    g.hist = b.hist; g.tile_sums = b.tile_sums;
+    AGC_COUNT_LAUNCH(1), k_keys_of_positions<<<scan_grid(n, sms), 256, 0, st>>>(ix, n, g.v[0], (unsigned*)g.k[0]);
+    int res2 = radix_sort_pairs<unsigned>(g, 0, n, 0, bits_for(r->size), nullptr, st);
+    AGC_COUNT_LAUNCH(1), k_sort_place<<<scan_grid(n, sms), 256, 0, st>>>(r->a, dtype_bytes(r->a_dtype), n, slot, g.v[res2], r->out);
+    return 0;
+  }
+  ScanParams p;
+  p.keys[0] = keys[0]; p.keys[1] = keys[1]; p.pos[0] = pos[0]; p.pos[1] = pos[1]; p.unsorted = flag;
+  p.a = r->a; p.a_dtype = r->a_dtype; p.out_dtype = r->out_dtype; p.out = r->out; p.n = n; p.flags = r->flags;
+  p.fill_f = r->fill_f64; p.fill_i = r->fill_i64;
+  p.a_float = dtype_is_float(r->a_dtype); p.a_u64 = r->a_dtype == AGC_DT_U64;
+  const bool facc = acc_is_float(r->op, r->a_dtype, r->out_dtype);
+  switch (r->op) {
+    case AGC_OP_CUMSUM: if (facc) run_seg_scan<double, SC_SUM>(p, ws, L, st); else run_seg_scan<long long, SC_SUM>(p, ws, L, st); break;
+    case AGC_OP_CUMPROD: if (facc) run_seg_scan<double, SC_PROD>(p, ws, L, st); else run_seg_scan<long long, SC_PROD>(p, ws, L, st); break;
+    case AGC_OP_CUMMAX: run_seg_scan<long long, SC_MAX>(p, ws, L, st); break;
+    case AGC_OP_CUMMIN: run_seg_scan<long long, SC_MIN>(p, ws, L, st); break;
+    default: g_scan_err = "unknown N->N op"; return -2;
+  }
+  return 0;
+}
+
+inline int group_order(const agc_index_t& index, int64_t n, int64_t size, long long* order, long long* offsets, void* workspace,
+                       int* status, cudaStream_t st, int sms) {
+  const ScanWs L = scan_ws_layout(n, false);
+  char* ws = (char*)workspace;
+  Indexer ix; ix.ix = index; ix.size = size; ix.n = n;
+  const unsigned* keys[2]; const unsigned* pos[2]; int* flag = nullptr;
+  int rc = group_sorted_pairs(ix, n, size, ws, L, status, false, st, sms, keys, pos, flag);
+  if (rc) return rc;
+  if (n > 0) AGC_COUNT_LAUNCH(1), k_order_widen<<<scan_grid(n, sms), 256, 0, st>>>(pos[0], pos[1], flag, n, order);
+  if (offsets) AGC_COUNT_LAUNCH(1), k_csr_offsets<<<scan_grid(size + 1, sms), 256, 0, st>>>(keys[0], keys[1], flag, n, size, offsets);
+  return 0;
+}
 
 }  // namespace agc

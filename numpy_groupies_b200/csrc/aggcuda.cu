@@ -28,6 +28,16 @@ int sm_count() {
   return g_sm_count;
 }
 
+bool g_profile = false;
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+bool g_ev_valid = false;
+void prof_begin(cudaStream_t st) {
+  if (!g_profile) return;
+  if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+  cudaEventRecord(g_ev0, st);
+}
+void prof_end(cudaStream_t st) { if (g_profile) { cudaEventRecord(g_ev1, st); g_ev_valid = true; } }
+
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Layout { int64_t t0, t1, t2, b0, b1, extra, total; };
@@ -74,7 +84,7 @@ int grid_for(int64_t work, int threads, int per_sm) {
 template <class T>
 void launch_accumulate(const agc::AccParams& p, cudaStream_t st) {
   if (p.n == 0) return;
-  agc::k_accumulate<T><<<grid_for(p.n, 256, 16), 256, 0, st>>>(p);
+  AGC_COUNT_LAUNCH(1), agc::k_accumulate<T><<<grid_for(p.n, 256, 16), 256, 0, st>>>(p);
 }
 void launch_accumulate_cls(const agc::AccParams& p, cudaStream_t st) {
   switch (p.a_dtype) {
@@ -155,27 +165,31 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
     if (!pass2_only) {
       if (!(r->flags & AGC_F_NO_FAST) && !(r->flags & AGC_F_NO_INIT) && r->size > 0 && r->n > 0) {
         // specialised shared-memory kernels (they initialise + write the same global tables)
+        prof_begin(st);
         int frc = agc::try_fast_path(r, t, st, sm_count());
         if (frc < 0) return fail(frc, "fast path launch failed");
         done = frc > 0;
+        if (done) prof_end(st);
         AGC_CUDA_OK("fast path");
       }
       if (!done) {
         if (!(r->flags & AGC_F_NO_INIT) && r->size > 0) {
-          agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
+          AGC_COUNT_LAUNCH(1), agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
           AGC_CUDA_OK("init");
         }
+        prof_begin(st);
         launch_accumulate_cls(p, st);
+        prof_end(st);
         AGC_CUDA_OK("accumulate");
       }
     }
     if (is_two_pass(r->op) && (pass2_only || fin)) {
       if (r->size > 0) {
         if (r->op == AGC_OP_VAR) {
-          agc::k_means_inplace<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size);
-          if (pass2_only) agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 1);
+          AGC_COUNT_LAUNCH(1), agc::k_means_inplace<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size);
+          if (pass2_only) AGC_COUNT_LAUNCH(1), agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 1);
         } else if (pass2_only) {
-          agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 1);
+          AGC_COUNT_LAUNCH(1), agc::k_init_tables<<<grid_for(r->size, 256, 8), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 1);
         }
       }
       p.pass = 2;
@@ -189,18 +203,28 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
     f.op = r->op; f.flags = r->flags; f.a_dtype = r->a_dtype; f.out_dtype = r->out_dtype; f.a = r->a; f.out = r->out;
     f.fill_f = r->fill_f64; f.fill_i = r->fill_i64; f.ddof = r->ddof; f.size = r->size; f.index_base = r->index_base;
     f.arg_stride = r->arg_stride; f.arg_len = r->arg_len; f.n = r->n; f.t = t;
-    agc::k_finalize<<<grid_for(r->size, 256, 8), 256, 0, st>>>(f);
+    AGC_COUNT_LAUNCH(1), agc::k_finalize<<<grid_for(r->size, 256, 8), 256, 0, st>>>(f);
     AGC_CUDA_OK("finalize");
   }
   return 0;
 }
 
+int agc_profile_enable(int on) { g_profile = on != 0; g_ev_valid = false; return 0; }
+float agc_profile_last_ms(void) {
+  if (!g_ev_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+  cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+  return ms;
+}
+int64_t agc_launch_count(void) { return agc::g_launches; }
+
 int agc_label_minmax(const void* labels, int32_t dtype, int64_t n, int64_t* out_minmax, void* stream) {
   if (n <= 0 || !labels || !out_minmax) return fail(-6, "agc_label_minmax: empty or null input");
   if (dtype < 0 || dtype > AGC_DT_U64) return fail(-3, "labels must have an integer dtype");
   cudaStream_t st = (cudaStream_t)stream;
-  agc::k_minmax_init<<<1, 1, 0, st>>>((long long*)out_minmax);
-  agc::k_label_minmax<<<grid_for(n, 256, 8), 256, 0, st>>>(labels, dtype, n, (long long*)out_minmax);
+  AGC_COUNT_LAUNCH(1), agc::k_minmax_init<<<1, 1, 0, st>>>((long long*)out_minmax);
+  AGC_COUNT_LAUNCH(1), agc::k_label_minmax<<<grid_for(n, 256, 8), 256, 0, st>>>(labels, dtype, n, (long long*)out_minmax);
   AGC_CUDA_OK("label_minmax");
   return 0;
 }
@@ -211,7 +235,7 @@ int agc_unpack(const void* table, int32_t elem_bytes, int64_t size, const void* 
   if (n == 0) return 0;
   if (!table || !labels || !out || !status) return fail(-6, "agc_unpack: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  agc::k_unpack<<<grid_for(n, 256, 16), 256, 0, st>>>(table, elem_bytes, size, labels, dtype, n, out, status);
+  AGC_COUNT_LAUNCH(1), agc::k_unpack<<<grid_for(n, 256, 16), 256, 0, st>>>(table, elem_bytes, size, labels, dtype, n, out, status);
   AGC_CUDA_OK("unpack");
   return 0;
 }

@@ -1,0 +1,181 @@
+"""GPU parity at sizes where the shared-memory fast kernels and the multi-tile scan / sort paths
+engage (the golden cases are all small): aggregate_cuda vs the oracle on seeded inputs, plus
+size-independent properties at the benchmark's full size."""
+import numpy as np
+import pytest
+
+from numpy_groupies_b200 import aggregate
+from oracle import aggregate_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _labels(rng, n, groups, dist):
+    if dist == "uniform":
+        return rng.integers(0, groups, n)
+    if dist == "zipf":
+        w = 1.0 / np.arange(1, groups + 1) ** 1.1
+        ranks = np.searchsorted(np.cumsum(w) / w.sum(), rng.random(n))
+        return rng.permutation(groups)[np.minimum(ranks, groups - 1)]
+    if dist == "sorted":
+        return np.sort(rng.integers(0, groups, n))
+    raise ValueError(dist)
+
+
+FAST_FUNCS = ["sum", "mean", "max", "min", "len", "sumofsquares", "var", "std", "nansum", "nanmean", "nanmax", "nanmin",
+              "nanlen", "nanvar"]
+
+
+@pytest.mark.parametrize("dist", ["uniform", "zipf", "sorted"])
+@pytest.mark.parametrize("groups", [100, 5000, 40000, 300000])
+@pytest.mark.parametrize("func", FAST_FUNCS)
+def test_f32_reductions_vs_oracle(func, groups, dist):
+    rng = np.random.default_rng(hash((func, groups, dist)) % 2**32)
+    n = 1 << 20
+    gidx = _labels(rng, n, groups, dist)
+    a = rng.standard_normal(n).astype(np.float32) * 3 + 1
+    if "nan" in func:
+        a[rng.random(n) < 0.1] = np.nan
+    got = aggregate(gidx, a, func=func, size=groups, fill_value=-1)
+    ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=-1)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    if func in ("max", "min", "nanmax", "nanmin", "len", "nanlen"):
+        np.testing.assert_array_equal(got, ref)            # bit-exact
+    else:
+        # fp32 tolerance from BASELINE.json north_star: rtol 1e-5 (atol guards cancellation around 0)
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("labels_dtype", [np.int32, np.int64])
+def test_fast_path_is_taken_and_matches_general_path(labels_dtype):
+    rng = np.random.default_rng(5)
+    n, groups = 1 << 21, 1000
+    gidx = rng.integers(0, groups, n).astype(labels_dtype)
+    a = rng.random(n, dtype=np.float32)
+    for func in ("sum", "mean", "max", "min", "len"):
+        fast = aggregate(gidx, a, func=func, size=groups)
+        slow = aggregate(gidx, a, func=func, size=groups, fast=False)
+        if func in ("max", "min", "len"):
+            np.testing.assert_array_equal(fast, slow)
+        else:
+            np.testing.assert_allclose(fast, slow, rtol=1e-6)
+
+
+def test_fixed_point_sum_is_exact_for_dyadic_data():
+    """torch.rand-style values k*2^-24 convert exactly into the fixed-point window, so the fast sum equals
+    the exactly-rounded result: compare against an integer sum."""
+    rng = np.random.default_rng(11)
+    n, groups = 1 << 22, 257
+    k = rng.integers(0, 1 << 24, n)
+    a = (k * 2.0 ** -24).astype(np.float32)
+    gidx = rng.integers(0, groups, n)
+    got = aggregate(gidx, a, func="sum", size=groups, dtype=np.float64)
+    exact = np.bincount(gidx, weights=k.astype(np.float64), minlength=groups) * 2.0 ** -24
+    np.testing.assert_array_equal(got, exact)
+
+
+def test_wide_dynamic_range_goes_through_the_exact_bypass():
+    rng = np.random.default_rng(12)
+    n, groups = 1 << 20, 64
+    a = (rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)).astype(np.float32)
+    a[::1001] = np.inf
+    a[5::1003] = -np.inf
+    gidx = rng.integers(0, groups, n)
+    got = aggregate(gidx, a, func="sum", size=groups, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        ref = oracle.aggregate(gidx, a, func="sum", size=groups, dtype=np.float64)
+    np.testing.assert_allclose(got, ref, rtol=1e-9, equal_nan=True)
+
+
+def test_bad_labels_raise_on_the_fast_path():
+    rng = np.random.default_rng(13)
+    n, groups = 1 << 20, 100
+    gidx = rng.integers(0, groups, n)
+    a = rng.random(n, dtype=np.float32)
+    for bad in (-1, groups):
+        g2 = gidx.copy(); g2[n // 3] = bad
+        with pytest.raises(ValueError):
+            aggregate(g2, a, func="sum", size=groups)
+
+
+@pytest.mark.parametrize("func", ["cumsum", "cummax", "cummin", "cumprod", "sort"])
+@pytest.mark.parametrize("dist", ["uniform", "sorted"])
+def test_int64_n_to_n_bit_exact(func, dist):
+    rng = np.random.default_rng(21)
+    n, groups = 1 << 20, 3000
+    gidx = _labels(rng, n, groups, dist)
+    a = rng.integers(-2**31, 2**31, n) if func != "cumprod" else rng.integers(-3, 4, n)
+    got = aggregate(gidx, a, func=func, size=groups)
+    ref = oracle.aggregate(gidx, a, func=func, size=groups)
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("func", ["first", "last", "argmax", "argmin", "nanargmax", "any", "all", "prod", "nanfirst"])
+def test_other_reductions_f64(func):
+    rng = np.random.default_rng(31)
+    n, groups = 1 << 20, 20000
+    gidx = rng.integers(0, groups, n)
+    a = rng.standard_normal(n)
+    if func == "prod":
+        a = 1 + a * 1e-3
+    if "nan" in func:
+        a[rng.random(n) < 0.1] = np.nan
+    if func in ("any", "all"):
+        a = (a > -1.5)
+    got = aggregate(gidx, a, func=func, size=groups)
+    ref = oracle.aggregate(gidx, a, func=func, size=groups)
+    assert got.dtype == ref.dtype
+    if func == "prod":
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+    else:
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_config3_var_std_nanmean_f64():
+    """BASELINE config 3 at reduced N: f64, 10 % NaN, many groups, ddof=1, rtol 1e-12."""
+    rng = np.random.default_rng(41)
+    n, groups = 1 << 21, 100000
+    gidx = rng.integers(0, groups, n)
+    a = rng.random(n)
+    a[rng.random(n) < 0.1] = np.nan
+    for func, kw in (("nanvar", dict(ddof=1)), ("nanstd", dict(ddof=1)), ("nanmean", {}), ("var", dict(ddof=1))):
+        got = aggregate(gidx, a, func=func, size=groups, fill_value=np.nan, **kw)
+        with np.errstate(all="ignore"):
+            ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=np.nan, **kw)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-15, equal_nan=True)
+
+
+def test_form3_and_form4_large():
+    rng = np.random.default_rng(51)
+    a = rng.random((64, 4096), dtype=np.float32)
+    gidx = rng.integers(0, 37, 4096)
+    for func in ("sum", "mean", "max"):
+        got = aggregate(gidx, a, func=func, axis=1, size=37)
+        ref = oracle.aggregate(gidx, a, func=func, axis=1, size=37)
+        np.testing.assert_allclose(got, ref, rtol=1e-5)
+    g2 = rng.integers(0, 256, (2, 1 << 20))
+    v = rng.random(1 << 20, dtype=np.float32)
+    for func in ("sum", "mean"):
+        got = aggregate(g2, v, func=func, size=(256, 256))
+        ref = oracle.aggregate(g2, v, func=func, size=(256, 256))
+        np.testing.assert_allclose(got, ref, rtol=1e-5)
+
+
+def test_full_size_properties_device_resident():
+    """N = 2^28 on the device: linearity / conservation properties that need no CPU oracle."""
+    import torch
+    n, groups = 1 << 28, 1000
+    g = torch.Generator(device="cuda").manual_seed(100)
+    gidx = torch.randint(0, groups, (n,), generator=g, device="cuda")
+    a = torch.rand(n, generator=g, device="cuda")
+    s = aggregate(gidx, a, func="sum", size=groups)
+    c = aggregate(gidx, a, func="len", size=groups)
+    m = aggregate(gidx, a, func="mean", size=groups)
+    mx = aggregate(gidx, a, func="max", size=groups)
+    assert int(c.sum()) == n                                            # counts conserve N (bit-exact)
+    torch.testing.assert_close(s.double().sum(), a.double().sum(), rtol=1e-6, atol=0)   # sum of sums
+    torch.testing.assert_close(m.double(), (s.double() / c.double()), rtol=1e-6, atol=0)
+    assert float(mx.max()) == float(a.max())                            # max of maxes
+    s2 = aggregate(gidx, 2 * a, func="sum", size=groups)                # linearity (exact: power-of-two scaling)
+    assert torch.equal(s2, 2 * s)

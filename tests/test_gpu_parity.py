@@ -19,8 +19,10 @@ G = Golden()
 #  * prod with floating `a` and an integer dtype: ufunc.at truncates after every multiply.
 def _divergent(case):
     cid = case["id"]
-    if "_sizesmall" in cid and "raises" not in case:
+    if "_sizesmall" in cid and "raises" not in case and int(G.arr(case["gidx"]).max()) >= 2:
         return "offset-recipe out-of-range labels: aggregate_cuda raises instead of corrupting"
+    if cid.startswith("dt_uint64_prod_as_int"):
+        return "reference result is overflow garbage (int * uint64 promotes to float64, RuntimeWarning: invalid)"
     if cid.endswith("_somenan") and case["func"] == "cumsum":
         return "reference leaks NaN across groups in float cumsum"
     if cid.startswith("dt_float") and "_prod_as_" in cid and ("int" in cid.split("_as_")[1] or "uint" in cid):
