@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda")
     ap.add_argument("--groups", type=int, default=100000)
@@ -107,9 +107,10 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc = [], None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -117,7 +118,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def wait_first(self, timeout=5.0):
+        t = time.time()
+        while not self.rows and time.time() - t < timeout:
+            time.sleep(0.02)
+
+    def mark(self, which):
+        setattr(self, which, time.time())
 
     def stop(self):
         if not self.proc:
@@ -129,7 +138,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (ts, r) in self.rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or ts) + 0.05]
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for k, nm in enumerate(names):
@@ -244,17 +254,23 @@ def main():
         step()
     barrier()
     lib.agc_profile_enable(1)
-    launches0 = lib.agc_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
+    launches0 = lib.agc_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     barrier()
+    if sampler:
+        sampler.mark("t0")
     ev0.record()
     for _ in range(args.steps):
         step()
         kernel_ms.append(lib.agc_profile_last_ms())
     ev1.record()
     barrier()
+    if sampler:
+        sampler.mark("t1")
     total_ms = ev0.elapsed_time(ev1)
     launches = lib.agc_launch_count() - launches0
     lib.agc_profile_enable(0)

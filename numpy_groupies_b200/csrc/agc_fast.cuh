@@ -39,6 +39,8 @@ struct FastParams {
   int square;           // sumofsquares: accumulate (float)(v*v)
   int want_b1;          // write touched flags (sum with fill != 0)
   int want_cnt;         // merge counts into T1 (mean / var)
+  int rshift;           // k_fast: log2(replicas of the table per CTA) -- kills same-address ATOMS conflicts under skew
+  int nslots;           // k_cache: slots of the per-CTA hot-key cache
 };
 
 __device__ __forceinline__ void fx_add(unsigned* lo, unsigned* hi, long long q) {
@@ -71,12 +73,14 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
-  const int G = (int)p.size;
+  const int rs = p.rshift;
+  const int G = (int)p.size << rs;                 // table entries incl. replicas: entry = (g << rs) | (lane & (R-1))
+  const int rsel = (threadIdx.x & 31) & ((1 << rs) - 1);
   unsigned* w0 = sw;            // sum.lo | key | count(FM_LEN)
   unsigned* w1 = sw + G;        // sum.hi
   unsigned* w2 = sw + 2 * G;    // count (FM_SUMCNT)
   const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
-  for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;
+  for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;   // G counts replicas
   if (threadIdx.x == 0) s_maxbits = 0u;
   __syncthreads();
 
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
 
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
-    const int gi = (int)g;
+    const int gi = ((int)g << rs) | rsel;
     if (MODE == FM_LEN) {
       if (LOAD_A && nanskip && x != x) return;
       atomicAdd(w0 + gi, 1u);
@@ -159,12 +163,17 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
   __syncthreads();
 
   // ---- merge the CTA's table into the global accumulator tables -----------------------------------
-  for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
+  // one thread per group: combine its replicas in shared memory, then ONE RED per touched group
+  const int R = 1 << rs;
+  for (int gi = threadIdx.x; gi < (int)p.size; gi += blockDim.x) {
+    const int e0 = gi << rs;
     if (MODE == FM_LEN) {
-      unsigned c = w0[gi];
-      if (c) atomicAdd((unsigned long long*)(p.t.t1 + gi), (unsigned long long)c);
+      unsigned long long c = 0;
+      for (int r = 0; r < R; ++r) c += w0[e0 + r];
+      if (c) atomicAdd((unsigned long long*)(p.t.t1 + gi), c);
     } else if (MODE == FM_MAX || MODE == FM_MIN) {
-      int k = (int)w0[gi];
+      int k = (int)init0;
+      for (int r = 0; r < R; ++r) { int kr = (int)w0[e0 + r]; k = MODE == FM_MAX ? max(k, kr) : min(k, kr); }
       if (k != (int)init0) {
         long long k64;
         if (MODE == FM_MAX) k64 = k == 0x7fffffff ? AGC_EMPTY_MIN : key_of((double)unkey_f32(k));
@@ -172,10 +181,141 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
         if (MODE == FM_MAX) atomicMax(p.t.t0i + gi, k64); else atomicMin(p.t.t0i + gi, k64);
       }
     } else {
-      long long q = (long long)(((unsigned long long)w1[gi] << 32) | w0[gi]);
+      long long q = 0; unsigned long long c = 0;
+      for (int r = 0; r < R; ++r) {
+        q += (long long)(((unsigned long long)w1[e0 + r] << 32) | w0[e0 + r]);     // <= 32 * 2^62 / 32: no overflow (FX_F headroom)
+        if (MODE == FM_SUMCNT) c += w2[e0 + r];
+      }
+      if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
+      if (MODE == FM_SUMCNT && c) {
+        if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + gi), c);
+        if (p.want_b1) p.t.b1[gi] = 1;
+      }
+    }
+  }
+}
+
+template <int MODE, class LT, bool LOAD_A>
+__global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
+  extern __shared__ unsigned sw[];
+  __shared__ unsigned s_maxbits;
+  constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
+  const unsigned S = (unsigned)p.nslots;
+  unsigned* tag = sw;             // 0 = free, else group + 1
+  unsigned* w0 = sw + S;
+  unsigned* w1 = sw + 2 * S;
+  unsigned* w2 = sw + 3 * S;
+  const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
+  for (unsigned i = threadIdx.x; i < (1 + WORDS) * S; i += blockDim.x) sw[i] = (i >= S && i < 2 * S) ? init0 : 0u;
+  if (threadIdx.x == 0) s_maxbits = 0u;
+  __syncthreads();
+
+  const long long nvec = p.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  bool bad = false;
+
+  unsigned lo_bits = 0, span_bits = 0; double scale = 1.0, inv_scale = 1.0;
+  if (MODE == FM_SUM || MODE == FM_SUMCNT) {
+    unsigned m = 0;
+    if (v < nvec) {
+      int4 av = ldg_stream16((const int4*)p.a + v);
+      unsigned b[4] = {(unsigned)av.x & 0x7fffffffu, (unsigned)av.y & 0x7fffffffu, (unsigned)av.z & 0x7fffffffu, (unsigned)av.w & 0x7fffffffu};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned bb = b[k];
+        if (p.square) { float f = __uint_as_float(bb); bb = __float_as_uint(f * f); }
+        if (bb < 0x7f800000u && bb > m) m = bb;
+      }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_maxbits, m);
+    __syncthreads();
+    int eb = (int)(s_maxbits >> 23);
+    if (eb == 0) eb = 127;
+    eb += 1;
+    int lo_e = eb - FX_WINDOW; if (lo_e < 1) lo_e = 1;
+    lo_bits = (unsigned)lo_e << 23;
+    span_bits = (unsigned)(eb - lo_e) << 23;
+    scale = __longlong_as_double((long long)(1023 + FX_F - (eb - 127)) << 52);
+    inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
+  }
+
+  auto update = [&](long long g, float x) {
+    if (g < 0 || g >= p.size) { bad = true; return; }
+    if (LOAD_A && x != x && nanskip) return;
+    if (MODE == FM_SUM || MODE == FM_SUMCNT) { if (p.square) x = x * x; }
+    // ---- cache lookup ----
+    const unsigned want = (unsigned)g + 1u;
+    const unsigned s = __umulhi((unsigned)g * 0x9E3779B1u, S);
+    unsigned t = tag[s];
+    if (t == 0u) { t = atomicCAS(tag + s, 0u, want); if (t == 0u) t = want; }
+    const bool hit = t == want;
+    if (MODE == FM_LEN) {
+      if (hit) atomicAdd(w0 + s, 1u); else atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull);
+    } else if (MODE == FM_MAX || MODE == FM_MIN) {
+      const bool nan = x != x;
+      if (hit) {
+        int k = nan ? (MODE == FM_MAX ? 0x7fffffff : (int)0x80000000) : key32_of(x);
+        if (MODE == FM_MAX) atomicMax((int*)w0 + s, k); else atomicMin((int*)w0 + s, k);
+      } else {
+        long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
+        if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64);
+      }
+    } else {
+      const unsigned ab = __float_as_uint(x) & 0x7fffffffu;
+      if (hit && (ab - lo_bits < span_bits)) {
+        fx_add(w0 + s, w1 + s, __double2ll_rn((double)x * scale));
+      } else if (ab != 0u) {
+        atomicAdd(p.t.t0f + g, (double)x);                 // miss, or outside the exact window
+      }
+      if (MODE == FM_SUMCNT) {
+        if (hit) atomicAdd(w2 + s, 1u);
+        else { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
+      }
+    }
+  };
+
+  for (; v < nvec; v += stride) {
+    long long g[4];
+    LabelVec<LT>::load(p.labels, v, g);
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (LOAD_A) {
+      int4 av = ldg_stream16((const int4*)p.a + v);
+      x[0] = __int_as_float(av.x); x[1] = __int_as_float(av.y); x[2] = __int_as_float(av.z); x[3] = __int_as_float(av.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) update(g[k], x[k]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
+    long long i = (nvec << 2) + threadIdx.x;
+    update(LabelVec<LT>::one(p.labels, i), LOAD_A ? p.a[i] : 0.f);
+  }
+  if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = 20 + MODE;
+  __syncthreads();
+
+  for (unsigned s = threadIdx.x; s < S; s += blockDim.x) {
+    const unsigned t = tag[s];
+    if (t == 0u) continue;
+    const long long gi = (long long)t - 1;
+    if (MODE == FM_LEN) {
+      unsigned c = w0[s];
+      if (c) atomicAdd((unsigned long long*)(p.t.t1 + gi), (unsigned long long)c);
+    } else if (MODE == FM_MAX || MODE == FM_MIN) {
+      int k = (int)w0[s];
+      if (k != (int)init0) {
+        long long k64;
+        if (MODE == FM_MAX) k64 = k == 0x7fffffff ? AGC_EMPTY_MIN : key_of((double)unkey_f32(k));
+        else k64 = k == (int)0x80000000 ? AGC_EMPTY_MAX : key_of((double)unkey_f32(k));
+        if (MODE == FM_MAX) atomicMax(p.t.t0i + gi, k64); else atomicMin(p.t.t0i + gi, k64);
+      }
+    } else {
+      long long q = (long long)(((unsigned long long)w1[s] << 32) | w0[s]);
       if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
       if (MODE == FM_SUMCNT) {
-        unsigned c = w2[gi];
+        unsigned c = w2[s];
         if (c) {
           if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + gi), (unsigned long long)c);
           if (p.want_b1) p.t.b1[gi] = 1;
@@ -183,6 +323,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
       }
     }
   }
+}
+
+template <int MODE, class LT, bool LOAD_A>
+inline int launch_cache(const FastParams& p, int ctas_per_sm, size_t smem, cudaStream_t st, int sms) {
+  auto kern = k_cache<MODE, LT, LOAD_A>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
+    attr_done = true;
+  }
+  AGC_COUNT_LAUNCH(1), kern<<<sms * ctas_per_sm, FAST_THREADS, smem, st>>>(p);
+  return 1;
 }
 
 template <int MODE, class LT, bool LOAD_A>
@@ -208,7 +360,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     return 0;
   const bool need_a = !is_len || nanskip;
   if (need_a && (r->a == nullptr || r->a_dtype != AGC_DT_F32)) return 0;
-  if (r->n < (1 << 16) || r->size > (1 << 16)) return 0;
+  if (r->n < (1 << 16) || r->size >= (1ll << 31)) return 0;
   if (((uintptr_t)r->index.labels & 15) || (need_a && ((uintptr_t)r->a & 15))) return 0;
   int mode;
   const bool want_b1 = (op == AGC_OP_SUM || op == AGC_OP_SUMSQ) && (r->flags & AGC_F_NEED_TOUCHED);
@@ -218,26 +370,51 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
   else mode = FM_SUM;
   const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
-  const size_t smem = (size_t)r->size * words * 4;
   const size_t cap2 = 110 * 1024, cap1 = 227 * 1024 - 1024;
-  if (smem > cap1) return 0;
-  const int ctas = smem <= cap2 ? 2 : 1;
-  if (r->n > (long long)sms * ctas * FAST_MAX_PER_CTA) return 0;
+  const size_t table = (size_t)r->size * words * 4;
+  const bool direct = table <= cap1;          // whole table privatised per CTA, else hot-key cache
+  static int env_cache_ctas = -1;
+  if (env_cache_ctas < 0) { const char* e = getenv("AGC_CACHE_CTAS"); env_cache_ctas = e ? atoi(e) : 2; if (env_cache_ctas != 1) env_cache_ctas = 2; }
 
   FastParams p;
   p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
   p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
   p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
+  p.rshift = 0; p.nslots = 0;
+  int ctas; size_t smem;
+  if (direct) {
+    ctas = table <= cap2 ? 2 : 1;
+    if (ctas == 2) while (p.rshift < 5 && (table << (p.rshift + 1)) <= cap2) ++p.rshift;   // replicate small tables
+    smem = table << p.rshift;
+  } else {
+    ctas = env_cache_ctas;
+    const size_t budget = ctas == 2 ? cap2 : cap1;
+    p.nslots = (int)(budget / ((1 + words) * 4));
+    smem = (size_t)p.nslots * (1 + words) * 4;
+  }
   AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
   const bool i64 = r->index.dtype == AGC_DT_I64;
   int rc = 0;
-#define AGC_FAST_CASE(M)                                                                          \
-  if (mode == M) {                                                                                \
-    if (i64) rc = need_a ? launch_fast<M, long long, true>(p, ctas, smem, st, sms) : launch_fast<M, long long, false>(p, ctas, smem, st, sms); \
-    else     rc = need_a ? launch_fast<M, int, true>(p, ctas, smem, st, sms) : launch_fast<M, int, false>(p, ctas, smem, st, sms);             \
+  // a CTA may take at most FAST_MAX_PER_CTA elements per launch (fixed-point / u32-count headroom): chunk N
+  const long long per_launch = (long long)sms * ctas * FAST_MAX_PER_CTA;
+  const long long n_total = r->n;
+  for (long long off = 0; off < n_total && rc >= 0; off += per_launch) {
+  p.n = n_total - off < per_launch ? n_total - off : per_launch;
+  p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
+  p.a = need_a ? (const float*)r->a + off : nullptr;
+#define AGC_FAST_CASE(M)                                                                                         \
+  if (mode == M) {                                                                                               \
+    if (direct) {                                                                                                \
+      if (i64) rc = need_a ? launch_fast<M, long long, true>(p, ctas, smem, st, sms) : launch_fast<M, long long, false>(p, ctas, smem, st, sms); \
+      else     rc = need_a ? launch_fast<M, int, true>(p, ctas, smem, st, sms) : launch_fast<M, int, false>(p, ctas, smem, st, sms);             \
+    } else {                                                                                                     \
+      if (i64) rc = need_a ? launch_cache<M, long long, true>(p, ctas, smem, st, sms) : launch_cache<M, long long, false>(p, ctas, smem, st, sms); \
+      else     rc = need_a ? launch_cache<M, int, true>(p, ctas, smem, st, sms) : launch_cache<M, int, false>(p, ctas, smem, st, sms);             \
+    }                                                                                                            \
   }
   AGC_FAST_CASE(FM_SUM) AGC_FAST_CASE(FM_SUMCNT) AGC_FAST_CASE(FM_MAX) AGC_FAST_CASE(FM_MIN) AGC_FAST_CASE(FM_LEN)
 #undef AGC_FAST_CASE
+  }
   return rc;
 }
 
