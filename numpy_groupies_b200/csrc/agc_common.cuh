@@ -168,4 +168,18 @@ __device__ __forceinline__ int4 ldg_stream16(const void* p) {
   return r;
 }
 
+// L2 eviction policy for data that is read exactly once: lets the streamed inputs leave L2 first so the
+// group tables (up to ~100 MB) stay resident while 12.9 GB of labels/values pass through.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int4 ldg_stream16_ef(const void* p, unsigned long long pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+
 }  // namespace agc

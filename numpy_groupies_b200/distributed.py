@@ -85,7 +85,9 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, dtype=N
     lab = ac._labels_on_device(c, device)
     vals = ac._values_on_device(c, device)
     plan = c.plan
-    offset, _total = shard_offsets(plan.n, group)
+    # global element indices only matter for first / last / arg*: everything else skips the all_gather
+    needs_offset = c.base in ("first", "last", "argmax", "argmin")
+    offset = shard_offsets(plan.n, group)[0] if needs_offset else 0
 
     compute_out = np.dtype(ac._COMPUTE_AS.get(c.out_dtype.name, c.out_dtype))
     req = _abi.Request()
@@ -143,7 +145,7 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, dtype=N
             run(base_flags | _abi.F_FIN_ONLY)
         if check:
             dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
-            if int(status[_abi.ST_BADLABEL].item()):
+            if int(status.cpu()[_abi.ST_BADLABEL]):           # the only host synchronisation of the call
                 raise ValueError("group_idx contains negative indices or indices too large for size")
     if c.out_dtype != compute_out:
         out = ac._Dev(out.t.to(getattr(torch, c.out_dtype.name)), c.out_dtype)

@@ -1,0 +1,55 @@
+"""Multi-GPU parity check, run under torchrun on >= 2 GPUs (not collected by pytest: needs several devices):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_gpu_check.py
+
+Every rank holds a contiguous shard; aggregate_sharded must reproduce the single-GPU aggregate of the
+concatenated data (bit-exact for integer / index / min / max results, 1e-12 for f64 sums)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from numpy_groupies_b200 import aggregate                     # noqa: E402
+from numpy_groupies_b200.distributed import aggregate_sharded  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    rng = np.random.default_rng(7)
+    n, groups = 1 << 21, 5000
+    gidx = rng.integers(0, groups - 50, n)
+    a64 = rng.standard_normal(n)
+    a64[rng.random(n) < 0.05] = np.nan
+    a32 = rng.random(n).astype(np.float32)
+    ai = rng.integers(-1000, 1000, n)
+    bounds = np.linspace(0, n, world + 1).astype(int)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    checked = 0
+    for func, arr, kw in (("sum", a32, {}), ("mean", a32, {}), ("max", a32, {}), ("min", a32, {}), ("len", a32, {}),
+                          ("nansum", a64, {}), ("nanmean", a64, {}), ("nanvar", a64, dict(ddof=1)), ("nanstd", a64, dict(ddof=1)),
+                          ("nanmax", a64, {}), ("nanargmax", a64, dict(fill_value=-1)), ("argmin", ai, dict(fill_value=-1)),
+                          ("first", ai, dict(fill_value=-7)), ("last", ai, dict(fill_value=-7)), ("sum", ai, dict(fill_value=3)),
+                          ("prod", 1 + a32 * 1e-3, {}), ("any", ai > 990, {}), ("all", ai > -990, dict(fill_value=1)),
+                          ("nanlen", a64, {}), ("sumofsquares", a32, {})):
+        full = aggregate(torch.from_numpy(gidx).cuda(), torch.from_numpy(arr).cuda(), func=func, size=groups, **kw).cpu().numpy()
+        part = aggregate_sharded(torch.from_numpy(gidx[lo:hi]).cuda(), torch.from_numpy(arr[lo:hi]).cuda(), func=func,
+                                 size=groups, **kw).cpu().numpy()
+        assert part.dtype == full.dtype and part.shape == full.shape, (func, part.dtype, full.dtype)
+        if full.dtype.kind == "f":
+            np.testing.assert_allclose(part, full, rtol=1e-12 if arr.dtype == np.float64 else 1e-6, equal_nan=True, err_msg=func)
+        else:
+            np.testing.assert_array_equal(part, full, err_msg=func)
+        checked += 1
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_gpu_check ok: {checked} functions, world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
