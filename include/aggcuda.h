@@ -117,7 +117,9 @@ typedef struct agc_request {
   void* workspace;                 /* device scratch, >= agc_workspace_bytes(req)                       */
   int64_t workspace_bytes;
   int32_t* status;                 /* device int32[8]; [0] bad label, [1] fast-path precision guard,    */
-                                   /* [2] labels-not-sorted (ASSUME_SORTED violated), [3] regime used   */
+                                   /* [2] labels-not-sorted (ASSUME_SORTED violated), [3] regime used,  */
+                                   /* [4..6] label probe: skewed?, largest bucket, equal neighbours;    */
+                                   /* [7] library scratch (work-item counter)                           */
 } agc_request_t;
 
 /* one partial table inside the workspace after AGC_F_ACC_ONLY (for the multi-GPU merge) */
@@ -154,6 +156,13 @@ int         agc_group_order(const agc_index_t* index, int64_t n, int64_t size, i
 int         agc_profile_enable(int on);
 float       agc_profile_last_ms(void);
 int64_t     agc_launch_count(void);
+/* kernel-selection knobs for A/B measurements and tests; value < 0 only reads.  Returns the (new) value.
+ *   key 0  strategy for tables larger than one SM's shared memory: 0 hot-key cache, 1 on-device label probe
+ *          decides (default), 2 always the cluster-partitioned table kernel, 3 always partial table + global RED
+ *   key 1  CTAs per SM of the hot-key-cache kernel (1 | 2)
+ *   key 2  kernel the probe picks for non-skewed labels (2 | 3, as key 0)
+ *   key 3  per-mille of the groups the cluster kernel keeps on chip */
+int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,7 @@ class Partial(C.Structure):
 
 EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_partials", "agc_aggregate",
            "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order",
-           "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count")
+           "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count", "agc_tuning")
 
 _lib = None
 
@@ -85,6 +85,8 @@ def load():
     lib.agc_profile_enable.argtypes = [C.c_int]
     lib.agc_profile_last_ms.restype = C.c_float
     lib.agc_launch_count.restype = C.c_int64
+    lib.agc_tuning.restype = C.c_int
+    lib.agc_tuning.argtypes = [C.c_int, C.c_int]
     if lib.agc_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libaggcuda ABI {lib.agc_abi_version()} != expected {ABI_VERSION}: rebuild")
     _lib = lib

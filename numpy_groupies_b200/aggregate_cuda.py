@@ -33,6 +33,21 @@ __all__ = ["aggregate", "unpack"]
 _torch = None
 
 
+_LAST = {"regime": 0, "probe": (0, 0, 0)}
+
+
+def last_regime():
+    """Which accumulate kernel the last checked call used (status[3] of the C ABI): 0 general global-table
+    kernel, 10+mode k_fast, 20+mode k_cache, 30+mode k_cluster (mode: 0 sum, 1 sum+count, 2 max, 3 min, 4 len)."""
+    return _LAST["regime"]
+
+
+def tuning(large=-1, cache_ctas=-1, uniform=-1, cover=-1):
+    """Kernel-selection knobs of libaggcuda (agc_tuning, include/aggcuda.h): for tests and A/B measurements."""
+    lib = _abi.load()
+    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, uniform, cover)))
+
+
 def _t():
     global _torch
     if _torch is None:
@@ -431,6 +446,8 @@ def _run_device(c):
             if st[_abi.ST_UNSORTED]:
                 raise ValueError("assume_sorted=True but group_idx is not sorted")
             c.regime = int(st[_abi.ST_REGIME])
+            _LAST["regime"] = c.regime
+            _LAST["probe"] = tuple(int(v) for v in st[4:7])
     if out_np_dtype != compute_out:                         # float16 results
         out = _Dev(out.t.to(getattr(torch, out_np_dtype.name)), out_np_dtype)
     return out

@@ -25,6 +25,9 @@ namespace agc {
 
 enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4 };
 
+// A narrower window (FX_F = 31: |q| < 2^31, the high word then moves only on a carry, ~1.25 ATOMS per element)
+// was measured and rejected: the 0.4 % of rand() values that fall below an 8-binade window take the global RED
+// bypass, and with few groups those REDs pile onto ~100 hot L2 addresses (sum G=100: 551 -> 356 Gelem/s).
 constexpr int FX_F = 40;          // fixed-point fraction bits below the reference exponent
 constexpr int FX_WINDOW = 16;     // binades that convert exactly: FX_F - 24
 constexpr int FAST_THREADS = 1024;
@@ -41,6 +44,9 @@ struct FastParams {
   int want_cnt;         // merge counts into T1 (mean / var)
   int rshift;           // k_fast: log2(replicas of the table per CTA) -- kills same-address ATOMS conflicts under skew
   int nslots;           // k_cache: slots of the per-CTA hot-key cache
+  int cov;              // k_fast: groups [0, cov) live in shared memory, the rest go straight to the global tables
+  const int* choose;    // k_cache: device word written by k_skew_probe; run iff *choose == want (NULL: always)
+  int want;
 };
 
 __device__ __forceinline__ void fx_add(unsigned* lo, unsigned* hi, long long q) {
@@ -70,11 +76,12 @@ template <> struct LabelVec<int> {
 
 template <int MODE, class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
+  if (p.choose && *p.choose != p.want) return;
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
   const int rs = p.rshift;
-  const int G = (int)p.size << rs;                 // table entries incl. replicas: entry = (g << rs) | (lane & (R-1))
+  const int G = p.cov << rs;                       // table entries incl. replicas: entry = (g << rs) | (lane & (R-1))
   const int rsel = (threadIdx.x & 31) & ((1 << rs) - 1);
   unsigned* w0 = sw;            // sum.lo | key | count(FM_LEN)
   unsigned* w1 = sw + G;        // sum.hi
@@ -120,6 +127,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
 
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
+    if (g >= p.cov) {                               // partial coverage (table larger than shared memory): global RED
+      const bool nan = x != x;
+      if (LOAD_A && nan && nanskip) return;
+      if (MODE == FM_LEN) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull);
+      else if (MODE == FM_MAX || MODE == FM_MIN) {
+        const long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
+        if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64);
+      } else {
+        if (p.square) x = x * x;
+        if ((__float_as_uint(x) & 0x7fffffffu) != 0u) atomicAdd(p.t.t0f + g, (double)x);
+        if (MODE == FM_SUMCNT) { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
+      }
+      return;
+    }
     const int gi = ((int)g << rs) | rsel;
     if (MODE == FM_LEN) {
       if (LOAD_A && nanskip && x != x) return;
@@ -165,7 +186,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
   // ---- merge the CTA's table into the global accumulator tables -----------------------------------
   // one thread per group: combine its replicas in shared memory, then ONE RED per touched group
   const int R = 1 << rs;
-  for (int gi = threadIdx.x; gi < (int)p.size; gi += blockDim.x) {
+  for (int gi = threadIdx.x; gi < p.cov; gi += blockDim.x) {
     const int e0 = gi << rs;
     if (MODE == FM_LEN) {
       unsigned long long c = 0;
@@ -197,6 +218,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
 
 template <int MODE, class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
+  if (p.choose && *p.choose != p.want) return;
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
@@ -347,75 +369,6 @@ inline int launch_fast(const FastParams& p, int ctas_per_sm, size_t smem, cudaSt
   }
   AGC_COUNT_LAUNCH(1), kern<<<sms * ctas_per_sm, FAST_THREADS, smem, st>>>(p);
   return 1;
-}
-
-// returns 1 if it accumulated into the global tables (which it also initialises), 0 to fall back
-inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
-  if (r->index.form != AGC_FORM_FLAT) return 0;
-  if (r->index.dtype != AGC_DT_I64 && r->index.dtype != AGC_DT_I32) return 0;
-  const int op = r->op;
-  const bool is_len = op == AGC_OP_LEN;
-  const bool nanskip = r->flags & AGC_F_NANSKIP;
-  if (!(op == AGC_OP_SUM || op == AGC_OP_SUMSQ || op == AGC_OP_MEAN || op == AGC_OP_MIN || op == AGC_OP_MAX || is_len || op == AGC_OP_VAR))
-    return 0;
-  const bool need_a = !is_len || nanskip;
-  if (need_a && (r->a == nullptr || r->a_dtype != AGC_DT_F32)) return 0;
-  if (r->n < (1 << 16) || r->size >= (1ll << 31)) return 0;
-  if (((uintptr_t)r->index.labels & 15) || (need_a && ((uintptr_t)r->a & 15))) return 0;
-  int mode;
-  const bool want_b1 = (op == AGC_OP_SUM || op == AGC_OP_SUMSQ) && (r->flags & AGC_F_NEED_TOUCHED);
-  if (is_len) mode = FM_LEN;
-  else if (op == AGC_OP_MAX) mode = FM_MAX;
-  else if (op == AGC_OP_MIN) mode = FM_MIN;
-  else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
-  else mode = FM_SUM;
-  const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
-  const size_t cap2 = 110 * 1024, cap1 = 227 * 1024 - 1024;
-  const size_t table = (size_t)r->size * words * 4;
-  const bool direct = table <= cap1;          // whole table privatised per CTA, else hot-key cache
-  static int env_cache_ctas = -1;
-  if (env_cache_ctas < 0) { const char* e = getenv("AGC_CACHE_CTAS"); env_cache_ctas = e ? atoi(e) : 2; if (env_cache_ctas != 1) env_cache_ctas = 2; }
-
-  FastParams p;
-  p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
-  p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
-  p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
-  p.rshift = 0; p.nslots = 0;
-  int ctas; size_t smem;
-  if (direct) {
-    ctas = table <= cap2 ? 2 : 1;
-    if (ctas == 2) while (p.rshift < 5 && (table << (p.rshift + 1)) <= cap2) ++p.rshift;   // replicate small tables
-    smem = table << p.rshift;
-  } else {
-    ctas = env_cache_ctas;
-    const size_t budget = ctas == 2 ? cap2 : cap1;
-    p.nslots = (int)(budget / ((1 + words) * 4));
-    smem = (size_t)p.nslots * (1 + words) * 4;
-  }
-  AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
-  const bool i64 = r->index.dtype == AGC_DT_I64;
-  int rc = 0;
-  // a CTA may take at most FAST_MAX_PER_CTA elements per launch (fixed-point / u32-count headroom): chunk N
-  const long long per_launch = (long long)sms * ctas * FAST_MAX_PER_CTA;
-  const long long n_total = r->n;
-  for (long long off = 0; off < n_total && rc >= 0; off += per_launch) {
-  p.n = n_total - off < per_launch ? n_total - off : per_launch;
-  p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
-  p.a = need_a ? (const float*)r->a + off : nullptr;
-#define AGC_FAST_CASE(M)                                                                                         \
-  if (mode == M) {                                                                                               \
-    if (direct) {                                                                                                \
-      if (i64) rc = need_a ? launch_fast<M, long long, true>(p, ctas, smem, st, sms) : launch_fast<M, long long, false>(p, ctas, smem, st, sms); \
-      else     rc = need_a ? launch_fast<M, int, true>(p, ctas, smem, st, sms) : launch_fast<M, int, false>(p, ctas, smem, st, sms);             \
-    } else {                                                                                                     \
-      if (i64) rc = need_a ? launch_cache<M, long long, true>(p, ctas, smem, st, sms) : launch_cache<M, long long, false>(p, ctas, smem, st, sms); \
-      else     rc = need_a ? launch_cache<M, int, true>(p, ctas, smem, st, sms) : launch_cache<M, int, false>(p, ctas, smem, st, sms);             \
-    }                                                                                                            \
-  }
-  AGC_FAST_CASE(FM_SUM) AGC_FAST_CASE(FM_SUMCNT) AGC_FAST_CASE(FM_MAX) AGC_FAST_CASE(FM_MIN) AGC_FAST_CASE(FM_LEN)
-#undef AGC_FAST_CASE
-  }
-  return rc;
 }
 
 }  // namespace agc

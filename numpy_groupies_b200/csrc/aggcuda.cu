@@ -6,6 +6,7 @@
 #include "agc_common.cuh"
 #include "agc_generic.cuh"
 #include "agc_fast.cuh"
+#include "agc_cluster.cuh"
 #include "agc_scan.cuh"
 
 namespace {
@@ -218,6 +219,12 @@ float agc_profile_last_ms(void) {
   return ms;
 }
 int64_t agc_launch_count(void) { return agc::g_launches; }
+int agc_tuning(int key, int value) {
+  agc::tuning_defaults();
+  if (key < 0 || key >= agc::TUNE_COUNT) return -1;
+  if (value >= 0) agc::g_tune[key] = value;
+  return agc::g_tune[key];
+}
 
 int agc_label_minmax(const void* labels, int32_t dtype, int64_t n, int64_t* out_minmax, void* stream) {
   if (n <= 0 || !labels || !out_minmax) return fail(-6, "agc_label_minmax: empty or null input");

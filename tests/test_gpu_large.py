@@ -179,3 +179,140 @@ def test_full_size_properties_device_resident():
     assert float(mx.max()) == float(a.max())                            # max of maxes
     s2 = aggregate(gidx, 2 * a, func="sum", size=groups)                # linearity (exact: power-of-two scaling)
     assert torch.equal(s2, 2 * s)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cluster-partitioned table kernel (agc_cluster.cuh): tables between one SM's shared memory and eight SMs'
+# ---------------------------------------------------------------------------------------------------------
+CLUSTER_FUNCS = ["sum", "mean", "max", "min", "len", "sumofsquares", "var", "nansum", "nanmean", "nanmax", "nanlen"]
+
+
+@pytest.fixture(params=[2, 3], ids=["cluster", "partial"])
+def force_large(request):
+    """Force the kernel used for tables larger than one SM's shared memory: 2 = k_cluster, 3 = partial k_fast."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    ac.tuning(large=request.param)
+    yield ac, request.param
+    ac.tuning(large=1)
+
+
+@pytest.mark.parametrize("dist", ["uniform", "zipf", "sorted"])
+@pytest.mark.parametrize("groups", [40000, 100000, 230000])
+@pytest.mark.parametrize("func", CLUSTER_FUNCS)
+def test_large_table_kernels_vs_oracle(func, groups, dist, force_large):
+    """Forced onto k_cluster / partial k_fast for every label distribution (the probe would send skewed / sorted
+    labels to the hot-key cache): same tolerances as the other f32 reductions; the regime word proves which ran."""
+    ac, strategy = force_large
+    rng = np.random.default_rng(hash((func, groups, dist, "cl")) % 2**32)
+    n = (1 << 21) + 3                                       # several phases per CTA + a ragged tail
+    gidx = _labels(rng, n, groups, dist)
+    a = rng.standard_normal(n).astype(np.float32) * 3 + 1
+    if "nan" in func:
+        a[rng.random(n) < 0.1] = np.nan
+    a[::4099] *= 1e12                                       # out-of-window values take the exact bypass
+    got = aggregate(gidx, a, func=func, size=groups, fill_value=-1)
+    regime = ac.last_regime()
+    ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=-1)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    words = {"sum": 3, "nansum": 3, "sumofsquares": 3, "mean": 3, "nanmean": 3, "var": 3}.get(func, 1)   # fill=-1: sum+count
+    if groups * words * 4 > 226 * 1024:                     # table larger than one SM's shared memory
+        assert regime // 10 == (3 if strategy == 2 else 1), regime
+    if func in ("max", "min", "nanmax", "len", "nanlen"):
+        np.testing.assert_array_equal(got, ref)
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("cover", [300, 700])
+def test_cluster_kernel_partial_coverage(cover):
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(78)
+    n, groups = (1 << 21) + 1, 100000
+    gidx = rng.integers(0, groups, n)
+    a = rng.standard_normal(n).astype(np.float32)
+    a[rng.random(n) < 0.05] = np.nan
+    try:
+        ac.tuning(large=2, cover=cover)
+        for func in ("sum", "nanmean", "max", "nanmin", "len", "nanlen"):
+            got = aggregate(gidx, a, func=func, size=groups)
+            assert ac.last_regime() // 10 == 3
+            with np.errstate(all="ignore"):
+                ref = oracle.aggregate(gidx, a, func=func, size=groups)
+            if func in ("max", "nanmin", "len", "nanlen"):
+                np.testing.assert_array_equal(got, ref)
+            else:
+                np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(ref)), equal_nan=True)
+    finally:
+        ac.tuning(large=1, cover=1000)
+
+
+def test_probe_routes_uniform_and_skewed_labels():
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(77)
+    n, groups = 1 << 21, 100000
+    a = rng.random(n, dtype=np.float32)
+    seen = {}
+    for dist in ("uniform", "zipf", "sorted"):
+        gidx = _labels(rng, n, groups, dist)
+        got = aggregate(gidx, a, func="sum", size=groups)
+        seen[dist] = ac.last_regime()
+        np.testing.assert_allclose(got, oracle.aggregate(gidx, a, func="sum", size=groups), rtol=1e-5)
+    assert seen["uniform"] in (10, 30) and seen["zipf"] == 20 and seen["sorted"] == 20, seen
+
+
+def test_large_table_kernels_full_size_agree():
+    """N = 2^28, 10^5 groups, device resident: many phases and several in-kernel merges; k_cluster and the partial
+    k_fast against k_cache (bit-exact for max / len; sums are exact fixed point up to the final f64 RED order)."""
+    import torch
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    n, groups = 1 << 28, 100000
+    g = torch.Generator(device="cuda").manual_seed(100)
+    gidx = torch.randint(0, groups, (n,), generator=g, device="cuda")
+    a = torch.rand(n, generator=g, device="cuda")
+    res = {}
+    try:
+        for mode in (2, 3, 0):
+            ac.tuning(large=mode)
+            for func in ("sum", "mean", "max", "min", "len"):
+                res[mode, func] = aggregate(gidx, a, func=func, size=groups)
+                assert (ac.last_regime() // 10) == {2: 3, 3: 1, 0: 2}[mode], (mode, func, ac.last_regime())
+    finally:
+        ac.tuning(large=1)
+    for mode in (2, 3):
+        for func in ("max", "min", "len"):
+            assert torch.equal(res[mode, func], res[0, func]), (mode, func)
+        for func in ("sum", "mean"):
+            torch.testing.assert_close(res[mode, func], res[0, func], rtol=1e-6, atol=0)
+    assert int(res[2, "len"].sum()) == n
+
+
+@pytest.mark.parametrize("func", ["sum", "mean", "max", "min", "nansum", "nanmean", "nanmax", "var", "sumofsquares"])
+@pytest.mark.parametrize("shape,groups", [((37, 8192), 100), ((5, 4, 4096), 1000), ((2, 65536), 9000)])
+def test_form3_last_axis_fast_path(func, shape, groups):
+    """Form 3 on the last axis of a C-contiguous f32 array: the row-block kernel (regime 40+mode) vs the oracle."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(hash((func, shape, groups)) % 2**32)
+    a = (rng.standard_normal(shape) * 2 + 0.5).astype(np.float32)
+    if "nan" in func:
+        a[rng.random(shape) < 0.1] = np.nan
+    a.reshape(-1)[::5003] *= 1e10
+    gidx = rng.integers(0, groups, shape[-1])
+    got = aggregate(gidx, a, func=func, axis=-1, size=groups, fill_value=-3)
+    assert ac.last_regime() // 10 == 4, ac.last_regime()
+    with np.errstate(all="ignore"):
+        ref = oracle.aggregate(gidx, a, func=func, axis=-1, size=groups, fill_value=-3)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    if func in ("max", "min", "nanmax"):
+        np.testing.assert_array_equal(got, ref)
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
+def test_form3_fast_path_bad_label_and_int32_labels():
+    rng = np.random.default_rng(61)
+    a = rng.random((16, 8192), dtype=np.float32)
+    gidx = rng.integers(0, 50, 8192).astype(np.int32)
+    np.testing.assert_allclose(aggregate(gidx, a, func="sum", axis=1, size=50), oracle.aggregate(gidx, a, func="sum", axis=1, size=50), rtol=1e-5)
+    g2 = gidx.copy(); g2[4000] = 50
+    with pytest.raises(ValueError):
+        aggregate(g2, a, func="sum", axis=1, size=50)
