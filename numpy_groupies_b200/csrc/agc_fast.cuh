@@ -45,7 +45,7 @@ struct FastParams {
   int rshift;           // k_fast: log2(replicas of the table per CTA) -- kills same-address ATOMS conflicts under skew
   int nslots;           // k_cache: slots of the per-CTA hot-key cache
   int cov;              // k_fast: groups [0, cov) live in shared memory, the rest go straight to the global tables
-  const int* choose;    // k_cache: device word written by k_skew_probe; run iff *choose == want (NULL: always)
+  const int* choose;    // device word written by k_skew_probe; run iff *choose == want (NULL: always)
   int want;
 };
 
@@ -74,8 +74,11 @@ template <> struct LabelVec<int> {
   static __device__ __forceinline__ long long one(const void* base, long long i) { return ((const int*)base)[i]; }
 };
 
-template <int MODE, class LT, bool LOAD_A>
-__global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
+// U = 128-bit value vectors per thread per iteration: U = 1 runs 2 CTAs/SM (32 registers), U = 2 runs 1 CTA/SM with
+// twice the loads in flight per thread (tables between 110 and 226 KB, and the partial / paired modes).
+// PARTIAL: the table covers only groups [0, cov) (size too large for shared memory); the rest are global REDs.
+template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL>
+__global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const FastParams p) {
   if (p.choose && *p.choose != p.want) return;
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
@@ -125,22 +128,23 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
     inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
   }
 
+  // accumulate straight into the global tables (uncovered groups, ragged tail)
+  auto direct_global = [&](long long g, float x) {
+    const bool nan = x != x;
+    if (LOAD_A && nan && nanskip) return;
+    if (MODE == FM_LEN) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull);
+    else if (MODE == FM_MAX || MODE == FM_MIN) {
+      const long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
+      if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64);
+    } else {
+      if (p.square) x = x * x;
+      if ((__float_as_uint(x) & 0x7fffffffu) != 0u) atomicAdd(p.t.t0f + g, (double)x);
+      if (MODE == FM_SUMCNT) { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
+    }
+  };
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
-    if (g >= p.cov) {                               // partial coverage (table larger than shared memory): global RED
-      const bool nan = x != x;
-      if (LOAD_A && nan && nanskip) return;
-      if (MODE == FM_LEN) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull);
-      else if (MODE == FM_MAX || MODE == FM_MIN) {
-        const long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
-        if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64);
-      } else {
-        if (p.square) x = x * x;
-        if ((__float_as_uint(x) & 0x7fffffffu) != 0u) atomicAdd(p.t.t0f + g, (double)x);
-        if (MODE == FM_SUMCNT) { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
-      }
-      return;
-    }
+    if (PARTIAL && g >= p.cov) { direct_global(g, x); return; }
     const int gi = ((int)g << rs) | rsel;
     if (MODE == FM_LEN) {
       if (LOAD_A && nanskip && x != x) return;
@@ -164,16 +168,27 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
     }
   };
 
-  for (; v < nvec; v += stride) {
-    long long g[4];
-    LabelVec<LT>::load(p.labels, v, g);
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    if (LOAD_A) {
-      int4 av = ldg_stream16((const int4*)p.a + v);
-      x[0] = __int_as_float(av.x); x[1] = __int_as_float(av.y); x[2] = __int_as_float(av.z); x[3] = __int_as_float(av.w);
+  for (; v < nvec; v += stride * U) {
+    long long g[U][4]; float x[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vu = v + u * stride;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { g[u][k] = 0; x[u][k] = 0.f; }
+      if (u == 0 || vu < nvec) {
+        LabelVec<LT>::load(p.labels, vu, g[u]);
+        if (LOAD_A) {
+          int4 av = ldg_stream16((const int4*)p.a + vu);
+          x[u][0] = __int_as_float(av.x); x[u][1] = __int_as_float(av.y); x[u][2] = __int_as_float(av.z); x[u][3] = __int_as_float(av.w);
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) update(g[k], x[k]);
+    for (int u = 0; u < U; ++u) {
+      if (u > 0 && v + u * stride >= nvec) break;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) update(g[u][k], x[u][k]);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {          // tail elements
     long long i = (nvec << 2) + threadIdx.x;
@@ -186,8 +201,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_fast(const FastParams p) {
   // ---- merge the CTA's table into the global accumulator tables -----------------------------------
   // one thread per group: combine its replicas in shared memory, then ONE RED per touched group
   const int R = 1 << rs;
-  for (int gi = threadIdx.x; gi < p.cov; gi += blockDim.x) {
-    const int e0 = gi << rs;
+  for (int gl = threadIdx.x; gl < p.cov; gl += blockDim.x) {
+    const int e0 = gl << rs;
+    const int gi = gl;
     if (MODE == FM_LEN) {
       unsigned long long c = 0;
       for (int r = 0; r < R; ++r) c += w0[e0 + r];
@@ -359,16 +375,22 @@ inline int launch_cache(const FastParams& p, int ctas_per_sm, size_t smem, cudaS
   return 1;
 }
 
-template <int MODE, class LT, bool LOAD_A>
-inline int launch_fast(const FastParams& p, int ctas_per_sm, size_t smem, cudaStream_t st, int sms) {
-  auto kern = k_fast<MODE, LT, LOAD_A>;
+template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL>
+inline int launch_fast_u(const FastParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = k_fast<MODE, LT, LOAD_A, U, PARTIAL>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
     attr_done = true;
   }
-  AGC_COUNT_LAUNCH(1), kern<<<sms * ctas_per_sm, FAST_THREADS, smem, st>>>(p);
+  AGC_COUNT_LAUNCH(1), kern<<<grid, FAST_THREADS, smem, st>>>(p);
   return 1;
+}
+template <int MODE, class LT, bool LOAD_A>
+inline int launch_fast(const FastParams& p, int ctas_per_sm, size_t smem, cudaStream_t st, int sms) {
+  const int grid = sms * ctas_per_sm;
+  if (p.cov < p.size) return launch_fast_u<MODE, LT, LOAD_A, 2, true>(p, grid, smem, st);      // always 1 CTA/SM
+  return ctas_per_sm == 1 ? launch_fast_u<MODE, LT, LOAD_A, 2, false>(p, grid, smem, st) : launch_fast_u<MODE, LT, LOAD_A, 1, false>(p, grid, smem, st);
 }
 
 }  // namespace agc
