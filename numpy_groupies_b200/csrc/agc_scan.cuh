@@ -108,59 +108,115 @@ inline void exclusive_scan_u32(unsigned* v, long long n, unsigned* tile_sums, cu
 }
 
 // ---------------------------------------------------------------------------------------------
-// radix sort-by-key: one 8-bit pass = histogram -> scan -> stable scatter
+// radix sort-by-key: one 8-bit pass = tile histograms -> device-wide scan -> stable scatter.
+// A tile is RS_THREADS x ITEMS consecutive elements; warp w owns the w-th contiguous slice of it and walks it in
+// items of 32 consecutive elements, so (tile, warp, item, lane) order == element order and ranks are stable:
+//   rank inside an item   MATCH.ANY on the digit (peers before me),
+//   rank inside the warp  per-warp digit counters in shared memory (only the owning warp touches them: no block sync),
+//   rank inside the tile  one pass over the 256 digits x warps after a single __syncthreads.
+// The tile is then written to shared memory in digit order and copied out from there, so every store instruction
+// covers whole runs of a digit (consecutive addresses) instead of 32 scattered words.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256, RS_CHUNKS = 32, RS_TILE = RS_THREADS * RS_CHUNKS;
-inline int rs_blocks(long long n) { return (int)((n + RS_TILE - 1) / RS_TILE); }
+constexpr int RS_THREADS = 512, RS_WARPS = RS_THREADS / 32;
+template <class K> struct RsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8; static constexpr int TILE = RS_THREADS * ITEMS; };
+constexpr int RS_TILE_MIN = RS_THREADS * 8;                 // smallest tile of any key type: sizes the histogram workspace
+inline int rs_blocks(long long n) { return (int)((n + RS_TILE_MIN - 1) / RS_TILE_MIN); }
+template <class K> inline int rs_blocks_k(long long n) { return (int)((n + RsCfg<K>::TILE - 1) / RsCfg<K>::TILE); }
 
 template <class K>
-__global__ void k_radix_hist(const K* keys, long long n, int shift, unsigned* hist, int nblocks, const int* run_flag) {
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long long n, int shift, unsigned* hist, int nblocks, const int* run_flag) {
   if (run_flag && *run_flag == 0) return;
   __shared__ unsigned h[256];
-  h[threadIdx.x] = 0;
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
   __syncthreads();
-  const long long base = (long long)blockIdx.x * RS_TILE;
-  for (int c = 0; c < RS_CHUNKS; ++c) {
-    long long i = base + c * RS_THREADS + threadIdx.x;
+  const long long base = (long long)blockIdx.x * RsCfg<K>::TILE;
+#pragma unroll 4
+  for (int c = 0; c < RsCfg<K>::ITEMS; ++c) {
+    const long long i = base + c * RS_THREADS + threadIdx.x;
     if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 0xffu], 1u);
   }
   __syncthreads();
-  hist[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  if (threadIdx.x < 256) hist[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
 template <class K>
-__global__ void k_radix_scatter(const K* kin, const unsigned* vin, K* kout, unsigned* vout, long long n, int shift,
-                                const unsigned* offs, int nblocks, const int* run_flag) {
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K* kin, const unsigned* vin, K* kout, unsigned* vout, long long n, int shift,
+                                                             const unsigned* offs, int nblocks, const int* run_flag) {
   if (run_flag && *run_flag == 0) return;
-  __shared__ unsigned running[256];
-  __shared__ unsigned warp_cnt[RS_THREADS / 32][256];
+  constexpr int ITEMS = RsCfg<K>::ITEMS, TILE = RsCfg<K>::TILE;
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  K* skey = (K*)rs_smem;                                          // [TILE] tile in digit order
+  unsigned* sval = (unsigned*)(skey + TILE);                      // [TILE]
+  unsigned* cnt = sval + TILE;                                    // [RS_WARPS][256] per-warp digit counters -> tile-local bases
+  unsigned* dstart = cnt + RS_WARPS * 256;                        // [256] tile-local start of every digit
+  unsigned* gbase = dstart + 256;                                 // [256] global position of the digit's first element of this tile
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  running[threadIdx.x] = offs[(long long)threadIdx.x * nblocks + blockIdx.x];
-  for (int k = 0; k < RS_THREADS / 32; ++k) warp_cnt[k][threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) cnt[i] = 0;
   __syncthreads();
-  const long long base = (long long)blockIdx.x * RS_TILE;
-  for (int c = 0; c < RS_CHUNKS; ++c) {
-    long long i = base + c * RS_THREADS + threadIdx.x;
+  const long long tile0 = (long long)blockIdx.x * TILE;
+  const long long wbase = tile0 + (long long)w * (ITEMS * 32);
+  K key[ITEMS]; unsigned val[ITEMS]; unsigned short rnk[ITEMS];
+  unsigned* mycnt = cnt + w * 256;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const long long i = wbase + j * 32 + lane;
     const bool valid = i < n;
-    K key = valid ? kin[i] : K(0);
-    unsigned val = valid ? vin[i] : 0u;
-    unsigned d = valid ? ((unsigned)(key >> shift) & 0xffu) : (256u + lane);
-    unsigned peers = __match_any_sync(0xffffffffu, d);
-    unsigned rank = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank == 0) warp_cnt[w][d] = __popc(peers);
-    __syncthreads();
-    if (valid) {
-      unsigned off = running[d] + rank;
-      for (int k = 0; k < w; ++k) off += warp_cnt[k][d];
-      kout[off] = key; vout[off] = val;
+    key[j] = valid ? kin[i] : K(0);
+    val[j] = valid ? vin[i] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool valid = wbase + j * 32 + lane < n;
+    const unsigned d = valid ? ((unsigned)(key[j] >> shift) & 0xffu) : (256u + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    unsigned old = 0;
+    if (lane == leader && valid) { old = mycnt[d]; mycnt[d] = old + __popc(peers); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rnk[j] = (unsigned short)(old + __popc(peers & lt));
+    __syncwarp();
+  }
+  __syncthreads();
+  // digit d: exclusive scan over the warps, tile-local digit start, global base
+  if (threadIdx.x < 256) {
+    unsigned run = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; ++k) { const unsigned c = cnt[k * 256 + threadIdx.x]; cnt[k * 256 + threadIdx.x] = run; run += c; }
+    dstart[threadIdx.x] = run;                                    // count for now
+    gbase[threadIdx.x] = offs[(long long)threadIdx.x * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+  if (w == 0) {                                                   // exclusive scan of the 256 digit counts (8 per lane)
+    unsigned c[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = dstart[lane * 8 + k]; s += c[k]; }
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    unsigned run = inc - s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dstart[lane * 8 + k] = run; run += c[k]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    if (wbase + j * 32 + lane < n) {
+      const unsigned d = (unsigned)(key[j] >> shift) & 0xffu;
+      const unsigned lp = dstart[d] + mycnt[d] + rnk[j];
+      skey[lp] = key[j]; sval[lp] = val[j];
     }
-    __syncthreads();
-    unsigned add = 0;
-    for (int k = 0; k < RS_THREADS / 32; ++k) { add += warp_cnt[k][threadIdx.x]; warp_cnt[k][threadIdx.x] = 0; }
-    running[threadIdx.x] += add;
-    __syncthreads();
+  }
+  __syncthreads();
+  const int count = (int)(n - tile0 < TILE ? n - tile0 : TILE);
+  for (int lp = threadIdx.x; lp < count; lp += RS_THREADS) {
+    const K k = skey[lp];
+    const unsigned d = (unsigned)(k >> shift) & 0xffu;
+    const long long pos = (long long)gbase[d] + (lp - dstart[d]);
+    kout[pos] = k; vout[pos] = sval[lp];
   }
 }
+template <class K> inline size_t rs_scatter_smem() { return (size_t)RsCfg<K>::TILE * (sizeof(K) + 4) + (RS_WARPS * 256 + 512) * 4; }
 
 struct SortBufs {
   void* k[2]; unsigned* v[2]; unsigned* hist; unsigned* tile_sums;
@@ -170,11 +226,13 @@ struct SortBufs {
 template <class K>
 inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int hi_bit, const int* run_flag, cudaStream_t st) {
   if (n == 0) return src;
-  const int nb = rs_blocks(n);
+  const int nb = rs_blocks_k<K>(n);
+  static bool attr_done = false;
+  if (!attr_done) { cudaFuncSetAttribute(k_radix_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<K>()); attr_done = true; }
   for (int shift = lo_bit; shift < hi_bit; shift += 8) {
     AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<nb, RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, run_flag);
     exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st);
-    AGC_COUNT_LAUNCH(1), k_radix_scatter<K><<<nb, RS_THREADS, 0, st>>>((const K*)b.k[src], b.v[src], (K*)b.k[src ^ 1], b.v[src ^ 1], n, shift,
+    AGC_COUNT_LAUNCH(1), k_radix_scatter<K><<<nb, RS_THREADS, rs_scatter_smem<K>(), st>>>((const K*)b.k[src], b.v[src], (K*)b.k[src ^ 1], b.v[src ^ 1], n, shift,
                                                    b.hist, nb, run_flag);
     src ^= 1;
   }
@@ -184,7 +242,8 @@ inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int h
 // ---------------------------------------------------------------------------------------------
 // key generation: flat group of every element (+ sortedness + bad-label detection)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_group_keys(Indexer ix, long long n, unsigned* keys, unsigned* pos, int* status, int* unsorted) {
+__global__ void k_group_keys(Indexer ix, long long n, unsigned* keys, unsigned* pos, int* status, int* unsorted, int only_if_unsorted) {
+  if (only_if_unsorted && *unsorted == 0) return;          // the direct (sorted-label) scan already produced the result
   const long long stride = (long long)gridDim.x * blockDim.x;
   bool bad = false, uns = false;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -223,6 +282,8 @@ struct ScanParams {
   double fill_f; long long fill_i;
   int a_float;                                        // value class of a
   int a_u64;
+  const void* labels; long long size; int* status; int* unsorted_w;   // direct (sorted flat labels) path
+  int only_if_unsorted;                               // keys path: no-op when the direct path already ran
 };
 
 // element k of the sorted sequence -> the value fed to the scan (A = double for float sum/prod,
@@ -321,6 +382,7 @@ template <class A, int OP, int PHASE>
 __global__ void __launch_bounds__(SG_THREADS) k_seg_scan(const ScanParams p, unsigned char* tile_f, A* tile_x,
                                                          const unsigned char* carry_ok, const A* carry_x) {
   const int sel = *p.unsorted ? 1 : 0;
+  if (p.only_if_unsorted && !sel) return;
   const unsigned* keys = p.keys[sel]; const unsigned* pos = p.pos[sel];
   const long long base = (long long)blockIdx.x * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
   A x[SG_ITEMS]; bool h[SG_ITEMS]; unsigned ps[SG_ITEMS];
@@ -364,37 +426,148 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan(const ScanParams p, uns
   }
 }
 
-// single block: inclusive segmented scan over tile aggregates -> carry for tile t = inclusive[t-1]
-template <class A, int OP>
-__global__ void k_seg_scan_tiles(const unsigned char* tile_f, const A* tile_x, int ntiles, unsigned char* carry_ok, A* carry_x) {
-  __shared__ unsigned char sf[1024];
-  __shared__ long long sx[1024];
-  const int per = (ntiles + blockDim.x - 1) / blockDim.x;
-  const int b = threadIdx.x * per;
-  bool f = false; A x = A(0); bool any = false;
-  for (int k = 0; k < per && b + k < ntiles; ++k) {
-    bool kf = tile_f[b + k]; A kx = tile_x[b + k];
-    if (!any) { f = kf; x = kx; any = true; } else { if (kf) x = kx; else x = ScanOp<A, OP>::apply(x, kx); f = f | kf; }
-  }
-  sf[threadIdx.x] = any ? f : 1; ((A*)sx)[threadIdx.x] = x;
-  __syncthreads();
-  // serial prefix over threads by thread 0..: 1024 entries, done cooperatively with a simple scan by one warp
-  if (threadIdx.x == 0) {
-    bool rf = false; A rx = A(0); bool have = false;
-    for (int t = 0; t < (int)blockDim.x; ++t) {
-      bool kf = sf[t]; A kx = ((A*)sx)[t];
-      // store EXCLUSIVE prefix for thread t
-      sf[t] = have ? 1 : 0; A keep = rx;
-      if (!have) { rf = kf; rx = kx; have = true; } else { if (kf) rx = kx; else rx = ScanOp<A, OP>::apply(rx, kx); rf = rf | kf; }
-      ((A*)sx)[t] = keep;
+// Direct variant for flat int32/int64 labels that are already non-decreasing: no keys, no positions, no sort.
+// PHASE 0 reads (label, value) once for the tile aggregates and, on the way, verifies sortedness and label
+// bounds; PHASE 1 re-reads them, applies the carry and writes out[i] -- 40 B/element instead of the 64+ of the
+// keys path.  If PHASE 0 finds an inversion it raises *unsorted and PHASE 1 returns at once; the sort-based path,
+// gated on the same flag, then does the work.
+template <class LT> __device__ __forceinline__ void load_labels8(const void* labels, long long base, long long n, long long (&g)[SG_ITEMS]);
+template <> __device__ __forceinline__ void load_labels8<long long>(const void* labels, long long base, long long n, long long (&g)[SG_ITEMS]) {
+  if (base + SG_ITEMS <= n) {
+    const int4* q = (const int4*)((const long long*)labels + base);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS / 2; ++k) {
+      int4 v = q[k];
+      g[2 * k] = ((long long)(unsigned)v.x) | ((long long)v.y << 32); g[2 * k + 1] = ((long long)(unsigned)v.z) | ((long long)v.w << 32);
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) g[k] = base + k < n ? ((const long long*)labels)[base + k] : 0;
   }
-  __syncthreads();
-  bool have = sf[threadIdx.x]; A run = ((A*)sx)[threadIdx.x];
-  for (int k = 0; k < per && b + k < ntiles; ++k) {
-    carry_ok[b + k] = have; carry_x[b + k] = run;
-    bool kf = tile_f[b + k]; A kx = tile_x[b + k];
-    if (!have) { run = kx; have = true; } else { if (kf) run = kx; else run = ScanOp<A, OP>::apply(run, kx); }
+}
+template <> __device__ __forceinline__ void load_labels8<int>(const void* labels, long long base, long long n, long long (&g)[SG_ITEMS]) {
+  if (base + SG_ITEMS <= n) {
+    const int4* q = (const int4*)((const int*)labels + base);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS / 4; ++k) { int4 v = q[k]; g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) g[k] = base + k < n ? ((const int*)labels)[base + k] : 0;
+  }
+}
+
+template <class A, int OP, class LT, int PHASE>
+__global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams p, unsigned char* tile_f, A* tile_x,
+                                                                const unsigned char* carry_ok, const A* carry_x) {
+  if (PHASE == 1 && *p.unsorted) return;
+  const long long base = (long long)blockIdx.x * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
+  A x[SG_ITEMS]; bool h[SG_ITEMS];
+  long long g[SG_ITEMS];
+  load_labels8<LT>(p.labels, base, p.n, g);
+  long long prev = 0;
+  if (base > 0 && base - 1 < p.n) prev = sizeof(LT) == 8 ? ((const long long*)p.labels)[base - 1] : (long long)((const int*)p.labels)[base - 1];
+  bool tf = false; A tx = A(0); bool any = false, uns = false, bad = false;
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    const long long i = base + k;
+    if (i < p.n) {
+      h[k] = (i == 0) || g[k] != prev;
+      if (PHASE == 0) { uns |= i > 0 && g[k] < prev; bad |= g[k] < 0 || g[k] >= p.size; }
+      prev = g[k];
+      x[k] = scan_input<A, OP>(p, (unsigned)i, h[k]);
+      if (!any) { tf = h[k]; tx = x[k]; any = true; }
+      else { if (h[k]) tx = x[k]; else tx = ScanOp<A, OP>::apply(tx, x[k]); tf = tf | h[k]; }
+      x[k] = tx;                               // thread-local inclusive scan
+    } else { h[k] = true; x[k] = A(0); }
+  }
+  if (PHASE == 0) {
+    if (uns) *p.unsorted_w = 1;
+    if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  }
+  if (!any) { tf = true; tx = A(0); }
+  bool pf, have_p, agg_f; A px, agg_x;
+  block_seg_scan<A, OP>(tf, tx, pf, px, have_p, agg_f, agg_x);
+  if (PHASE == 0) {
+    if (threadIdx.x == 0) { tile_f[blockIdx.x] = agg_f; tile_x[blockIdx.x] = agg_x; }
+    return;
+  }
+  bool have_c = blockIdx.x > 0 && carry_ok[blockIdx.x];
+  A cx = have_c ? carry_x[blockIdx.x] : A(0);
+  bool have = false; A pre = A(0);
+  if (have_p) { pre = px; have = true; if (have_c && !pf) pre = ScanOp<A, OP>::apply(cx, px); }
+  else if (have_c) { pre = cx; have = true; }
+  bool open = have;
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    const long long i = base + k;
+    if (i >= p.n) break;
+    if (h[k]) open = false;
+    A r = open ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
+    scan_store<A, OP>(p, i, r);
+  }
+}
+
+// single block: segmented scan over the tile aggregates -> carry for tile t = aggregate of tiles [0, t).
+// (f, x) (+) (g, y) = (f | g, g ? y : op(x, y)).  Tile 0 always starts with a head flag, so every exclusive prefix
+// with t > 0 is well defined.  The tiles are walked in coalesced chunks of 1024 with a running carry; the next
+// chunk's loads are issued before the current chunk is scanned.
+template <class A, int OP>
+__global__ void __launch_bounds__(1024) k_seg_scan_tiles(const unsigned char* tile_f, const A* tile_x, int ntiles, unsigned char* carry_ok, A* carry_x,
+                                                         const int* run_flag, int run_if) {
+  if (run_flag && (*run_flag != 0) != (run_if != 0)) return;
+  __shared__ unsigned char sf[32];
+  __shared__ long long sx[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  bool rf = true; A rx = A(0);                               // running carry = aggregate of all earlier chunks
+  bool nf = true; A nx = A(0);
+  if (t < ntiles) { nf = tile_f[t]; nx = tile_x[t]; }
+  for (int c0 = 0; c0 < ntiles; c0 += 1024) {
+    const int idx = c0 + t;
+    const bool f = nf; const A x = nx;
+    const int nidx = idx + 1024;
+    nf = true; nx = A(0);
+    if (nidx < ntiles) { nf = tile_f[nidx]; nx = tile_x[nidx]; }
+    // inclusive segmented scan inside the warp
+    bool fi = f; A xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const bool ft = __shfl_up_sync(0xffffffffu, (int)fi, o);
+      const A xt = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
+    }
+    if (lane == 31) { sf[w] = fi; ((A*)sx)[w] = xi; }
+    bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); A xe = __shfl_up_sync(0xffffffffu, xi, 1);   // exclusive in warp (lane > 0)
+    __syncthreads();
+    if (w == 0) {                                            // scan of the 32 warp aggregates
+      bool af = sf[lane]; A ax = ((A*)sx)[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const bool ft = __shfl_up_sync(0xffffffffu, (int)af, o);
+        const A xt = __shfl_up_sync(0xffffffffu, ax, o);
+        if (lane >= o) { if (!af) ax = ScanOp<A, OP>::apply(xt, ax); af = af | ft; }
+      }
+      sf[lane] = af; ((A*)sx)[lane] = ax;                    // inclusive over warps
+    }
+    __syncthreads();
+    // exclusive prefix of this thread inside the chunk: warps before (+) lanes before
+    bool pf = false; A px = A(0); bool havep = false;
+    if (w > 0) { pf = sf[w - 1]; px = ((A*)sx)[w - 1]; havep = true; }
+    if (lane > 0) {
+      if (havep && !fe) { px = ScanOp<A, OP>::apply(px, xe); pf = pf | fe; }
+      else { px = xe; pf = fe | pf; }
+      havep = true;
+    }
+    // with the running carry of earlier chunks
+    bool ef; A ex;
+    if (havep) { ef = pf | (c0 > 0 && rf); ex = (c0 > 0 && !pf) ? ScanOp<A, OP>::apply(rx, px) : px; }
+    else { ef = rf; ex = rx; }
+    (void)ef;
+    if (idx < ntiles) { carry_ok[idx] = idx > 0; carry_x[idx] = ex; }
+    // new running carry = old (+) chunk aggregate (inclusive value of the last warp)
+    const bool cf = sf[31]; const A cx = ((A*)sx)[31];
+    if (c0 == 0) { rf = cf; rx = cx; }
+    else { if (!cf) rx = ScanOp<A, OP>::apply(rx, cx); else rx = cx; rf = rf | cf; }
+    __syncthreads();
   }
 }
 
@@ -487,12 +660,13 @@ inline int scan_grid(long long n, int sms) { long long b = (n + 255) / 256; long
 // through (keys[0|1], pos[0|1]) selected by *flag on the device.
 inline int group_sorted_pairs(const Indexer& ix, long long n, long long size, char* ws, const ScanWs& L, int* status,
                               bool assume_sorted, cudaStream_t st, int sms, const unsigned* (&keys)[2], const unsigned* (&pos)[2],
-                              int*& flag) {
+                              int*& flag, bool flag_ready = false) {
   if (n >= (1ll << 32) || size > (1ll << 32)) { g_scan_err = "N->N / sort paths support n < 2^32 and size <= 2^32"; return -21; }
   flag = (int*)(ws + L.flag);
-  AGC_COUNT_LAUNCH(1), k_zero_int<<<1, 1, 0, st>>>(flag);
+  // flag_ready: the direct scan already set *flag (1 = labels not sorted); everything below then only runs when it is 1
+  if (!flag_ready) AGC_COUNT_LAUNCH(1), k_zero_int<<<1, 1, 0, st>>>(flag);
   unsigned* k0 = (unsigned*)(ws + L.k32[0]); unsigned* p0 = (unsigned*)(ws + L.v[0]);
-  if (n > 0) AGC_COUNT_LAUNCH(1), k_group_keys<<<scan_grid(n, sms), 256, 0, st>>>(ix, n, k0, p0, status, flag);
+  if (n > 0) AGC_COUNT_LAUNCH(1), k_group_keys<<<scan_grid(n, sms), 256, 0, st>>>(ix, n, k0, p0, status, flag, flag_ready ? 1 : 0);
   SortBufs b; b.k[0] = k0; b.k[1] = ws + L.k32[1]; b.v[0] = p0; b.v[1] = (unsigned*)(ws + L.v[1]);
   b.hist = (unsigned*)(ws + L.hist); b.tile_sums = (unsigned*)(ws + L.tsum);
   int res = 0;
@@ -509,8 +683,34 @@ inline void run_seg_scan(const ScanParams& p, char* ws, const ScanWs& L, cudaStr
   unsigned char* tf = (unsigned char*)(ws + L.tile_f); A* tx = (A*)(ws + L.tile_x);
   unsigned char* cf = (unsigned char*)(ws + L.carry_f); A* cx = (A*)(ws + L.carry_x);
   AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 0><<<ntiles, SG_THREADS, 0, st>>>(p, tf, tx, nullptr, nullptr);
-  AGC_COUNT_LAUNCH(1), k_seg_scan_tiles<A, OP><<<1, 1024, 0, st>>>(tf, tx, ntiles, cf, cx);
+  AGC_COUNT_LAUNCH(1), k_seg_scan_tiles<A, OP><<<1, 1024, 0, st>>>(tf, tx, ntiles, cf, cx, p.only_if_unsorted ? p.unsorted : nullptr, 1);
   AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 1><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, nullptr, cf, cx);
+}
+
+template <class A, int OP, class LT>
+inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st) {
+  if (p.n == 0) return;
+  const int ntiles = (int)((p.n + SG_TILE - 1) / SG_TILE);
+  unsigned char* tf = (unsigned char*)(ws + L.tile_f); A* tx = (A*)(ws + L.tile_x);
+  unsigned char* cf = (unsigned char*)(ws + L.carry_f); A* cx = (A*)(ws + L.carry_x);
+  AGC_COUNT_LAUNCH(1), k_seg_scan_direct<A, OP, LT, 0><<<ntiles, SG_THREADS, 0, st>>>(p, tf, tx, nullptr, nullptr);
+  AGC_COUNT_LAUNCH(1), k_seg_scan_tiles<A, OP><<<1, 1024, 0, st>>>(tf, tx, ntiles, cf, cx, p.unsorted, 0);
+  AGC_COUNT_LAUNCH(1), k_seg_scan_direct<A, OP, LT, 1><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, nullptr, cf, cx);
+}
+template <class A, int OP>
+inline void run_seg_scan_any(const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st, int direct_lt) {
+  if (direct_lt == 8) run_seg_scan_direct<A, OP, long long>(p, ws, L, st);
+  else if (direct_lt == 4) run_seg_scan_direct<A, OP, int>(p, ws, L, st);
+  else run_seg_scan<A, OP>(p, ws, L, st);
+}
+inline void dispatch_seg_scan(const agc_request_t* r, const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st, int direct_lt) {
+  const bool facc = acc_is_float(r->op, r->a_dtype, r->out_dtype);
+  switch (r->op) {
+    case AGC_OP_CUMSUM: if (facc) run_seg_scan_any<double, SC_SUM>(p, ws, L, st, direct_lt); else run_seg_scan_any<long long, SC_SUM>(p, ws, L, st, direct_lt); break;
+    case AGC_OP_CUMPROD: if (facc) run_seg_scan_any<double, SC_PROD>(p, ws, L, st, direct_lt); else run_seg_scan_any<long long, SC_PROD>(p, ws, L, st, direct_lt); break;
+    case AGC_OP_CUMMAX: run_seg_scan_any<long long, SC_MAX>(p, ws, L, st, direct_lt); break;
+    default: run_seg_scan_any<long long, SC_MIN>(p, ws, L, st, direct_lt); break;
+  }
 }
 
 inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
@@ -522,7 +722,29 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
   char* ws = (char*)r->workspace;
   Indexer ix; ix.ix = r->index; ix.size = r->size; ix.n = n;
   const unsigned* keys[2]; const unsigned* pos[2]; int* flag = nullptr;
-  int rc = group_sorted_pairs(ix, n, r->size, ws, L, r->status, (r->flags & AGC_F_ASSUME_SORTED) != 0, st, sms, keys, pos, flag);
+  if (n >= (1ll << 32) || r->size > (1ll << 32)) { g_scan_err = "N->N / sort paths support n < 2^32 and size <= 2^32"; return -21; }
+
+  ScanParams p;
+  memset(&p, 0, sizeof(p));
+  p.a = r->a; p.a_dtype = r->a_dtype; p.out_dtype = r->out_dtype; p.out = r->out; p.n = n; p.flags = r->flags;
+  p.fill_f = r->fill_f64; p.fill_i = r->fill_i64;
+  p.a_float = dtype_is_float(r->a_dtype); p.a_u64 = r->a_dtype == AGC_DT_U64;
+  p.labels = r->index.labels; p.size = r->size; p.status = r->status;
+
+  // ---- flat int32/int64 labels: try the direct (already sorted) scan first -------------------------------
+  int direct_lt = 0;
+  if (!sort_op && n > 0 && r->index.form == AGC_FORM_FLAT && !((uintptr_t)r->index.labels & 15)) {
+    if (r->index.dtype == AGC_DT_I64) direct_lt = 8; else if (r->index.dtype == AGC_DT_I32) direct_lt = 4;
+  }
+  if (direct_lt) {
+    flag = (int*)(ws + L.flag);
+    AGC_COUNT_LAUNCH(1), k_zero_int<<<1, 1, 0, st>>>(flag);
+    p.unsorted = flag; p.unsorted_w = flag;
+    dispatch_seg_scan(r, p, ws, L, st, direct_lt);
+    if (r->flags & AGC_F_ASSUME_SORTED) { AGC_COUNT_LAUNCH(1), k_report_unsorted<<<1, 1, 0, st>>>(flag, r->status); return 0; }
+  }
+
+  int rc = group_sorted_pairs(ix, n, r->size, ws, L, r->status, (r->flags & AGC_F_ASSUME_SORTED) != 0, st, sms, keys, pos, flag, direct_lt != 0);
   if (rc) return rc;
   if (n == 0) return 0;
   if (sort_op) {
@@ -545,19 +767,10 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
     AGC_COUNT_LAUNCH(1), k_sort_place<<<scan_grid(n, sms), 256, 0, st>>>(r->a, dtype_bytes(r->a_dtype), n, slot, g.v[res2], r->out);
     return 0;
   }
-  ScanParams p;
   p.keys[0] = keys[0]; p.keys[1] = keys[1]; p.pos[0] = pos[0]; p.pos[1] = pos[1]; p.unsorted = flag;
-  p.a = r->a; p.a_dtype = r->a_dtype; p.out_dtype = r->out_dtype; p.out = r->out; p.n = n; p.flags = r->flags;
-  p.fill_f = r->fill_f64; p.fill_i = r->fill_i64;
-  p.a_float = dtype_is_float(r->a_dtype); p.a_u64 = r->a_dtype == AGC_DT_U64;
-  const bool facc = acc_is_float(r->op, r->a_dtype, r->out_dtype);
-  switch (r->op) {
-    case AGC_OP_CUMSUM: if (facc) run_seg_scan<double, SC_SUM>(p, ws, L, st); else run_seg_scan<long long, SC_SUM>(p, ws, L, st); break;
-    case AGC_OP_CUMPROD: if (facc) run_seg_scan<double, SC_PROD>(p, ws, L, st); else run_seg_scan<long long, SC_PROD>(p, ws, L, st); break;
-    case AGC_OP_CUMMAX: run_seg_scan<long long, SC_MAX>(p, ws, L, st); break;
-    case AGC_OP_CUMMIN: run_seg_scan<long long, SC_MIN>(p, ws, L, st); break;
-    default: g_scan_err = "unknown N->N op"; return -2;
-  }
+  p.only_if_unsorted = direct_lt != 0;
+  if (r->op < AGC_OP_CUMSUM || r->op > AGC_OP_CUMMIN) { g_scan_err = "unknown N->N op"; return -2; }
+  dispatch_seg_scan(r, p, ws, L, st, 0);
   return 0;
 }
 
