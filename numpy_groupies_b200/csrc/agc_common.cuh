@@ -20,6 +20,17 @@ namespace agc {
 static long long g_launches = 0;
 #define AGC_COUNT_LAUNCH(n_) (::agc::g_launches += (n_))
 
+// SM count of the current device (cached); grid cap for the tile-loop kernels
+inline int device_sms() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+inline int tile_grid(long long ntiles, int ctas_per_sm) {
+  const long long cap = (long long)device_sms() * ctas_per_sm;
+  return (int)(ntiles < 1 ? 1 : (ntiles < cap ? ntiles : cap));
+}
+
 // ---------------------------------------------------------------------------------------------
 // value classes: every input dtype is widened at load time to one of four classes
 // ---------------------------------------------------------------------------------------------

@@ -74,15 +74,22 @@ __device__ __forceinline__ unsigned block_exclusive_scan_u32(unsigned x, unsigne
   __syncthreads();
   return r;
 }
-__global__ void k_xs_reduce(const unsigned* v, long long n, unsigned* tile_sums) {
+// (all tile kernels below walk their tiles with a grid-stride loop over a grid capped at a few CTAs per SM: when a
+// device-side run_flag turns them into no-ops, an empty launch then costs microseconds instead of tens of them)
+__global__ void k_xs_reduce(const unsigned* v, long long n, unsigned* tile_sums, int ntiles, const int* run_flag) {
+  if (run_flag && *run_flag == 0) return;
   __shared__ unsigned tot;
-  long long base = (long long)blockIdx.x * XS_TILE + (long long)threadIdx.x * XS_ITEMS;
-  unsigned s = 0;
-  for (int k = 0; k < XS_ITEMS; ++k) if (base + k < n) s += v[base + k];
-  block_exclusive_scan_u32(s, &tot);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long base = (long long)tile * XS_TILE + (long long)threadIdx.x * XS_ITEMS;
+    unsigned s = 0;
+    for (int k = 0; k < XS_ITEMS; ++k) if (base + k < n) s += v[base + k];
+    block_exclusive_scan_u32(s, &tot);
+    if (threadIdx.x == 0) tile_sums[tile] = tot;
+    __syncthreads();
+  }
 }
-__global__ void k_xs_scan_sums(unsigned* tile_sums, int ntiles) {      // single block, serial-in-thread chunks
+__global__ void k_xs_scan_sums(unsigned* tile_sums, int ntiles, const int* run_flag) {      // single block, serial-in-thread chunks
+  if (run_flag && *run_flag == 0) return;
   __shared__ unsigned tot;
   const int per = (ntiles + blockDim.x - 1) / blockDim.x;
   const int b = threadIdx.x * per;
@@ -91,20 +98,23 @@ __global__ void k_xs_scan_sums(unsigned* tile_sums, int ntiles) {      // single
   unsigned run = block_exclusive_scan_u32(s, &tot);
   for (int k = 0; k < per; ++k) if (b + k < ntiles) { unsigned t = tile_sums[b + k]; tile_sums[b + k] = run; run += t; }
 }
-__global__ void k_xs_apply(unsigned* v, long long n, const unsigned* tile_sums) {
+__global__ void k_xs_apply(unsigned* v, long long n, const unsigned* tile_sums, int ntiles, const int* run_flag) {
+  if (run_flag && *run_flag == 0) return;
   __shared__ unsigned tot;
-  long long base = (long long)blockIdx.x * XS_TILE + (long long)threadIdx.x * XS_ITEMS;
-  unsigned x[XS_ITEMS], s = 0;
-  for (int k = 0; k < XS_ITEMS; ++k) { x[k] = base + k < n ? v[base + k] : 0; s += x[k]; }
-  unsigned run = block_exclusive_scan_u32(s, &tot) + tile_sums[blockIdx.x];
-  for (int k = 0; k < XS_ITEMS; ++k) if (base + k < n) { v[base + k] = run; run += x[k]; }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long base = (long long)tile * XS_TILE + (long long)threadIdx.x * XS_ITEMS;
+    unsigned x[XS_ITEMS], s = 0;
+    for (int k = 0; k < XS_ITEMS; ++k) { x[k] = base + k < n ? v[base + k] : 0; s += x[k]; }
+    unsigned run = block_exclusive_scan_u32(s, &tot) + tile_sums[tile];
+    for (int k = 0; k < XS_ITEMS; ++k) if (base + k < n) { v[base + k] = run; run += x[k]; }
+  }
 }
 inline long long xs_tiles(long long n) { return (n + XS_TILE - 1) / XS_TILE; }
-inline void exclusive_scan_u32(unsigned* v, long long n, unsigned* tile_sums, cudaStream_t st) {
+inline void exclusive_scan_u32(unsigned* v, long long n, unsigned* tile_sums, cudaStream_t st, const int* run_flag = nullptr) {
   int nt = (int)xs_tiles(n);
-  AGC_COUNT_LAUNCH(1), k_xs_reduce<<<nt, XS_THREADS, 0, st>>>(v, n, tile_sums);
-  AGC_COUNT_LAUNCH(1), k_xs_scan_sums<<<1, 1024, 0, st>>>(tile_sums, nt);
-  AGC_COUNT_LAUNCH(1), k_xs_apply<<<nt, XS_THREADS, 0, st>>>(v, n, tile_sums);
+  AGC_COUNT_LAUNCH(1), k_xs_reduce<<<tile_grid(nt, 8), XS_THREADS, 0, st>>>(v, n, tile_sums, nt, run_flag);
+  AGC_COUNT_LAUNCH(1), k_xs_scan_sums<<<1, 1024, 0, st>>>(tile_sums, nt, run_flag);
+  AGC_COUNT_LAUNCH(1), k_xs_apply<<<tile_grid(nt, 8), XS_THREADS, 0, st>>>(v, n, tile_sums, nt, run_flag);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +128,7 @@ inline void exclusive_scan_u32(unsigned* v, long long n, unsigned* tile_sums, cu
 // covers whole runs of a digit (consecutive addresses) instead of 32 scattered words.
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 512, RS_WARPS = RS_THREADS / 32;
-template <class K> struct RsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8; static constexpr int TILE = RS_THREADS * ITEMS; };
+template <class K> struct RsCfg { static constexpr int ITEMS = 8; static constexpr int TILE = RS_THREADS * ITEMS; };   // 16 items -> 128 registers, 1 CTA/SM: slower
 constexpr int RS_TILE_MIN = RS_THREADS * 8;                 // smallest tile of any key type: sizes the histogram workspace
 inline int rs_blocks(long long n) { return (int)((n + RS_TILE_MIN - 1) / RS_TILE_MIN); }
 template <class K> inline int rs_blocks_k(long long n) { return (int)((n + RsCfg<K>::TILE - 1) / RsCfg<K>::TILE); }
@@ -127,20 +137,23 @@ template <class K>
 __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long long n, int shift, unsigned* hist, int nblocks, const int* run_flag) {
   if (run_flag && *run_flag == 0) return;
   __shared__ unsigned h[256];
-  if (threadIdx.x < 256) h[threadIdx.x] = 0;
-  __syncthreads();
-  const long long base = (long long)blockIdx.x * RsCfg<K>::TILE;
+  for (int tile = blockIdx.x; tile < nblocks; tile += gridDim.x) {
+    if (threadIdx.x < 256) h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)tile * RsCfg<K>::TILE;
 #pragma unroll 4
-  for (int c = 0; c < RsCfg<K>::ITEMS; ++c) {
-    const long long i = base + c * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 0xffu], 1u);
+    for (int c = 0; c < RsCfg<K>::ITEMS; ++c) {
+      const long long i = base + c * RS_THREADS + threadIdx.x;
+      if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) hist[(long long)threadIdx.x * nblocks + tile] = h[threadIdx.x];
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x < 256) hist[(long long)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
 template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K* kin, const unsigned* vin, K* kout, unsigned* vout, long long n, int shift,
+__global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, const unsigned* vin, K* kout, unsigned* vout, long long n, int shift,
                                                              const unsigned* offs, int nblocks, const int* run_flag) {
   if (run_flag && *run_flag == 0) return;
   constexpr int ITEMS = RsCfg<K>::ITEMS, TILE = RsCfg<K>::TILE;
@@ -151,69 +164,72 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K* kin, cons
   unsigned* dstart = cnt + RS_WARPS * 256;                        // [256] tile-local start of every digit
   unsigned* gbase = dstart + 256;                                 // [256] global position of the digit's first element of this tile
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) cnt[i] = 0;
-  __syncthreads();
-  const long long tile0 = (long long)blockIdx.x * TILE;
-  const long long wbase = tile0 + (long long)w * (ITEMS * 32);
-  K key[ITEMS]; unsigned val[ITEMS]; unsigned short rnk[ITEMS];
-  unsigned* mycnt = cnt + w * 256;
-  const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const long long i = wbase + j * 32 + lane;
-    const bool valid = i < n;
-    key[j] = valid ? kin[i] : K(0);
-    val[j] = valid ? vin[i] : 0u;
-  }
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const bool valid = wbase + j * 32 + lane < n;
-    const unsigned d = valid ? ((unsigned)(key[j] >> shift) & 0xffu) : (256u + lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    unsigned old = 0;
-    if (lane == leader && valid) { old = mycnt[d]; mycnt[d] = old + __popc(peers); }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rnk[j] = (unsigned short)(old + __popc(peers & lt));
-    __syncwarp();
-  }
-  __syncthreads();
-  // digit d: exclusive scan over the warps, tile-local digit start, global base
-  if (threadIdx.x < 256) {
-    unsigned run = 0;
-#pragma unroll
-    for (int k = 0; k < RS_WARPS; ++k) { const unsigned c = cnt[k * 256 + threadIdx.x]; cnt[k * 256 + threadIdx.x] = run; run += c; }
-    dstart[threadIdx.x] = run;                                    // count for now
-    gbase[threadIdx.x] = offs[(long long)threadIdx.x * nblocks + blockIdx.x];
-  }
-  __syncthreads();
-  if (w == 0) {                                                   // exclusive scan of the 256 digit counts (8 per lane)
-    unsigned c[8], s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { c[k] = dstart[lane * 8 + k]; s += c[k]; }
-    unsigned inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    unsigned run = inc - s;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { dstart[lane * 8 + k] = run; run += c[k]; }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    if (wbase + j * 32 + lane < n) {
-      const unsigned d = (unsigned)(key[j] >> shift) & 0xffu;
-      const unsigned lp = dstart[d] + mycnt[d] + rnk[j];
-      skey[lp] = key[j]; sval[lp] = val[j];
+  for (int tile = blockIdx.x; tile < nblocks; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) cnt[i] = 0;
+    __syncthreads();
+    const long long tile0 = (long long)tile * TILE;
+    const long long wbase = tile0 + (long long)w * (ITEMS * 32);
+    K key[ITEMS]; unsigned val[ITEMS]; unsigned short rnk[ITEMS];
+    unsigned* mycnt = cnt + w * 256;
+    const unsigned lt = (1u << lane) - 1u;
+  #pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const long long i = wbase + j * 32 + lane;
+      const bool valid = i < n;
+      key[j] = valid ? kin[i] : K(0);
+      val[j] = valid ? vin[i] : 0u;
     }
-  }
-  __syncthreads();
-  const int count = (int)(n - tile0 < TILE ? n - tile0 : TILE);
-  for (int lp = threadIdx.x; lp < count; lp += RS_THREADS) {
-    const K k = skey[lp];
-    const unsigned d = (unsigned)(k >> shift) & 0xffu;
-    const long long pos = (long long)gbase[d] + (lp - dstart[d]);
-    kout[pos] = k; vout[pos] = sval[lp];
+  #pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const bool valid = wbase + j * 32 + lane < n;
+      const unsigned d = valid ? ((unsigned)(key[j] >> shift) & 0xffu) : (256u + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      unsigned old = 0;
+      if (lane == leader && valid) { old = mycnt[d]; mycnt[d] = old + __popc(peers); }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rnk[j] = (unsigned short)(old + __popc(peers & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+    // digit d: exclusive scan over the warps, tile-local digit start, global base
+    if (threadIdx.x < 256) {
+      unsigned run = 0;
+  #pragma unroll
+      for (int k = 0; k < RS_WARPS; ++k) { const unsigned c = cnt[k * 256 + threadIdx.x]; cnt[k * 256 + threadIdx.x] = run; run += c; }
+      dstart[threadIdx.x] = run;                                    // count for now
+      gbase[threadIdx.x] = offs[(long long)threadIdx.x * nblocks + tile];
+    }
+    __syncthreads();
+    if (w == 0) {                                                   // exclusive scan of the 256 digit counts (8 per lane)
+      unsigned c[8], s = 0;
+  #pragma unroll
+      for (int k = 0; k < 8; ++k) { c[k] = dstart[lane * 8 + k]; s += c[k]; }
+      unsigned inc = s;
+  #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      unsigned run = inc - s;
+  #pragma unroll
+      for (int k = 0; k < 8; ++k) { dstart[lane * 8 + k] = run; run += c[k]; }
+    }
+    __syncthreads();
+  #pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      if (wbase + j * 32 + lane < n) {
+        const unsigned d = (unsigned)(key[j] >> shift) & 0xffu;
+        const unsigned lp = dstart[d] + mycnt[d] + rnk[j];
+        skey[lp] = key[j]; sval[lp] = val[j];
+      }
+    }
+    __syncthreads();
+    const int count = (int)(n - tile0 < TILE ? n - tile0 : TILE);
+    for (int lp = threadIdx.x; lp < count; lp += RS_THREADS) {
+      const K k = skey[lp];
+      const unsigned d = (unsigned)(k >> shift) & 0xffu;
+      const long long pos = (long long)gbase[d] + (lp - dstart[d]);
+      kout[pos] = k; vout[pos] = sval[lp];
+    }
+    __syncthreads();
   }
 }
 template <class K> inline size_t rs_scatter_smem() { return (size_t)RsCfg<K>::TILE * (sizeof(K) + 4) + (RS_WARPS * 256 + 512) * 4; }
@@ -230,9 +246,9 @@ inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int h
   static bool attr_done = false;
   if (!attr_done) { cudaFuncSetAttribute(k_radix_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<K>()); attr_done = true; }
   for (int shift = lo_bit; shift < hi_bit; shift += 8) {
-    AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<nb, RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, run_flag);
-    exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st);
-    AGC_COUNT_LAUNCH(1), k_radix_scatter<K><<<nb, RS_THREADS, rs_scatter_smem<K>(), st>>>((const K*)b.k[src], b.v[src], (K*)b.k[src ^ 1], b.v[src ^ 1], n, shift,
+    AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<tile_grid(nb, 4), RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, run_flag);
+    exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st, run_flag);
+    AGC_COUNT_LAUNCH(1), k_radix_scatter<K><<<tile_grid(nb, 2), RS_THREADS, rs_scatter_smem<K>(), st>>>((const K*)b.k[src], b.v[src], (K*)b.k[src ^ 1], b.v[src ^ 1], n, shift,
                                                    b.hist, nb, run_flag);
     src ^= 1;
   }
@@ -284,6 +300,7 @@ struct ScanParams {
   int a_u64;
   const void* labels; long long size; int* status; int* unsorted_w;   // direct (sorted flat labels) path
   int only_if_unsorted;                               // keys path: no-op when the direct path already ran
+  void* gath;                                         // keys path: scan inputs in sorted order (PHASE 0 gathers them once)
 };
 
 // element k of the sorted sequence -> the value fed to the scan (A = double for float sum/prod,
@@ -395,7 +412,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan(const ScanParams p, uns
       unsigned key = keys[i];
       h[k] = (i == 0) || key != prev; prev = key;
       ps[k] = pos[i];
-      x[k] = scan_input<A, OP>(p, ps[k], h[k]);
+      if (PHASE == 0) { x[k] = scan_input<A, OP>(p, ps[k], h[k]); if (p.gath) ((A*)p.gath)[i] = x[k]; }   // the only random gather of a
+      else x[k] = p.gath ? ((const A*)p.gath)[i] : scan_input<A, OP>(p, ps[k], h[k]);
       if (!any) { tf = h[k]; tx = x[k]; any = true; }
       else { if (h[k]) tx = x[k]; else tx = ScanOp<A, OP>::apply(tx, x[k]); tf = tf | h[k]; }
       x[k] = tx;                               // thread-local inclusive scan
@@ -423,6 +441,56 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan(const ScanParams p, uns
     if (h[k]) open = false;
     A r = open ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
     scan_store<A, OP>(p, (long long)ps[k], r);
+  }
+}
+
+// ---- vectorised element access for the direct scan: 8 consecutive elements per thread as 128-bit loads ----
+__device__ __forceinline__ bool raw8_ok(int dt) { return dt == AGC_DT_I64 || dt == AGC_DT_U64 || dt == AGC_DT_F64 || dt == AGC_DT_F32 || dt == AGC_DT_I32 || dt == AGC_DT_U32; }
+__device__ __forceinline__ void load_raw8(const void* a, int dt, long long base, unsigned long long (&raw)[SG_ITEMS]) {
+  if (dtype_bytes(dt) == 8) {
+    const int4* q = (const int4*)((const unsigned long long*)a + base);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS / 2; ++k) {
+      const int4 v = q[k];
+      raw[2 * k] = ((unsigned long long)(unsigned)v.x) | ((unsigned long long)(unsigned)v.y << 32);
+      raw[2 * k + 1] = ((unsigned long long)(unsigned)v.z) | ((unsigned long long)(unsigned)v.w << 32);
+    }
+  } else {
+    const int4* q = (const int4*)((const unsigned*)a + base);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS / 4; ++k) {
+      const int4 v = q[k];
+      raw[4 * k] = (unsigned)v.x; raw[4 * k + 1] = (unsigned)v.y; raw[4 * k + 2] = (unsigned)v.z; raw[4 * k + 3] = (unsigned)v.w;
+    }
+  }
+}
+// same value semantics as scan_input, from the element's raw bits
+template <class A, int OP>
+__device__ __forceinline__ A scan_from_raw(const ScanParams& p, unsigned long long raw, bool head) {
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  const int dt = p.a_dtype;
+  const long long vi = dt == AGC_DT_I32 ? (long long)(int)(unsigned)raw : (long long)raw;      // U32 / U64 / I64: raw as is
+  if (OP == SC_SUM || OP == SC_PROD) {
+    if (std::is_same<A, double>::value) {
+      double v;
+      if (dt == AGC_DT_F32) v = (double)__uint_as_float((unsigned)raw);
+      else if (dt == AGC_DT_F64) v = __longlong_as_double((long long)raw);
+      else if (p.a_u64) v = (double)raw;
+      else v = (double)vi;
+      if (nanskip && v != v) v = OP == SC_SUM ? 0.0 : 1.0;
+      return (A)v;
+    } else {
+      return (A)vi;
+    }
+  } else {
+    const long long ident = OP == SC_MAX ? AGC_EMPTY_MAX : AGC_EMPTY_MIN;
+    const long long absorb = OP == SC_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX;
+    if (p.a_float) {
+      const double v = dt == AGC_DT_F32 ? (double)__uint_as_float((unsigned)raw) : __longlong_as_double((long long)raw);
+      if (v != v) return (A)((nanskip || !head) ? ident : absorb);
+      return (A)key_of(v);
+    }
+    return (A)(p.a_u64 ? key_of((unsigned long long)raw) : vi);
   }
 }
 
@@ -459,7 +527,9 @@ template <> __device__ __forceinline__ void load_labels8<int>(const void* labels
 template <class A, int OP, class LT, int PHASE>
 __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams p, unsigned char* tile_f, A* tile_x,
                                                                 const unsigned char* carry_ok, const A* carry_x) {
-  if (PHASE == 1 && *p.unsorted) return;
+  // PHASE 1: nothing to do when the labels are not sorted; PHASE 0: another tile already found an inversion.
+  // (block-uniform decision: every thread takes the same branch around the barriers below)
+  if (__syncthreads_or(*(volatile const int*)p.unsorted)) return;
   const long long base = (long long)blockIdx.x * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
   A x[SG_ITEMS]; bool h[SG_ITEMS];
   long long g[SG_ITEMS];
@@ -467,6 +537,9 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
   long long prev = 0;
   if (base > 0 && base - 1 < p.n) prev = sizeof(LT) == 8 ? ((const long long*)p.labels)[base - 1] : (long long)((const int*)p.labels)[base - 1];
   bool tf = false; A tx = A(0); bool any = false, uns = false, bad = false;
+  const bool vec = base + SG_ITEMS <= p.n && raw8_ok(p.a_dtype) && !((uintptr_t)p.a & 15);
+  unsigned long long raw[SG_ITEMS];
+  if (vec) load_raw8(p.a, p.a_dtype, base, raw);
 #pragma unroll
   for (int k = 0; k < SG_ITEMS; ++k) {
     const long long i = base + k;
@@ -474,7 +547,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
       h[k] = (i == 0) || g[k] != prev;
       if (PHASE == 0) { uns |= i > 0 && g[k] < prev; bad |= g[k] < 0 || g[k] >= p.size; }
       prev = g[k];
-      x[k] = scan_input<A, OP>(p, (unsigned)i, h[k]);
+      x[k] = vec ? scan_from_raw<A, OP>(p, raw[k], h[k]) : scan_input<A, OP>(p, (unsigned)i, h[k]);
       if (!any) { tf = h[k]; tx = x[k]; any = true; }
       else { if (h[k]) tx = x[k]; else tx = ScanOp<A, OP>::apply(tx, x[k]); tf = tf | h[k]; }
       x[k] = tx;                               // thread-local inclusive scan
@@ -497,13 +570,27 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
   if (have_p) { pre = px; have = true; if (have_c && !pf) pre = ScanOp<A, OP>::apply(cx, px); }
   else if (have_c) { pre = cx; have = true; }
   bool open = have;
+  // cumsum / cumprod into a 64-bit output of the accumulator's own class: results leave as 128-bit stores
+  const bool vst = (OP == SC_SUM || OP == SC_PROD) && base + SG_ITEMS <= p.n && !((uintptr_t)p.out & 15) &&
+                   (std::is_same<A, double>::value ? p.out_dtype == AGC_DT_F64 : (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64));
+  A res[SG_ITEMS];
 #pragma unroll
   for (int k = 0; k < SG_ITEMS; ++k) {
     const long long i = base + k;
     if (i >= p.n) break;
     if (h[k]) open = false;
     A r = open ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
-    scan_store<A, OP>(p, i, r);
+    res[k] = r;
+    if (!vst) scan_store<A, OP>(p, i, r);
+  }
+  if (vst) {
+    int4* q = (int4*)((A*)p.out + base);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS / 2; ++k) {
+      const long long b0 = std::is_same<A, double>::value ? __double_as_longlong((double)res[2 * k]) : (long long)res[2 * k];
+      const long long b1 = std::is_same<A, double>::value ? __double_as_longlong((double)res[2 * k + 1]) : (long long)res[2 * k + 1];
+      q[k] = make_int4((int)(unsigned)b0, (int)(b0 >> 32), (int)(unsigned)b1, (int)(b1 >> 32));
+    }
   }
 }
 
@@ -633,7 +720,7 @@ __global__ void k_pos_select(const unsigned* p0, const unsigned* p1, const int* 
 // ---------------------------------------------------------------------------------------------
 inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 struct ScanWs {
-  int64_t k32[2], v[2], k64[2], v2[2], slot, hist, tsum, tile_f, tile_x, carry_f, carry_x, flag, total;
+  int64_t k32[2], v[2], k64[2], v2[2], slot, gath, hist, tsum, tile_f, tile_x, carry_f, carry_x, flag, total;
 };
 inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   ScanWs w; int64_t o = 0;
@@ -642,6 +729,7 @@ inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   w.k32[0] = take(n * 4); w.k32[1] = take(n * 4); w.v[0] = take(n * 4); w.v[1] = take(n * 4);
   if (want_sort_op) { w.k64[0] = take(n * 8); w.k64[1] = take(n * 8); w.v2[0] = take(n * 4); w.v2[1] = take(n * 4); w.slot = take(n * 4); }
   else { w.k64[0] = w.k64[1] = w.v2[0] = w.v2[1] = w.slot = 0; }
+  w.gath = want_sort_op ? 0 : take(n * 8);
   w.hist = take(256ll * nb * 4); w.tsum = take((xs_tiles(256ll * nb) + 1) * 4);
   const long long ntiles = (n + SG_TILE - 1) / SG_TILE + 1;
   w.tile_f = take(ntiles); w.tile_x = take(ntiles * 8); w.carry_f = take(ntiles); w.carry_x = take(ntiles * 8);
@@ -769,6 +857,7 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
   }
   p.keys[0] = keys[0]; p.keys[1] = keys[1]; p.pos[0] = pos[0]; p.pos[1] = pos[1]; p.unsorted = flag;
   p.only_if_unsorted = direct_lt != 0;
+  p.gath = ws + L.gath;
   if (r->op < AGC_OP_CUMSUM || r->op > AGC_OP_CUMMIN) { g_scan_err = "unknown N->N op"; return -2; }
   dispatch_seg_scan(r, p, ws, L, st, 0);
   return 0;
