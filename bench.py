@@ -207,6 +207,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def dominant_kernel(regime):
+    fam = {0: "k_accumulate (global tables)", 1: "k_fast (shared-memory table; partial table + global RED when size exceeds one SM)",
+           2: "k_cache (per-CTA hot-key cache + global RED)", 3: "k_cluster (cluster-partitioned table)", 4: "k_form3"}.get(regime // 10, "?")
+    return f"accumulate stage of the step: {fam}, regime {regime}"
+
+
 def workload_config(args, n_override=None):
     n = n_override or (1 << args.log2n)
     return {"workload": f"form1_{args.func}_f32_int64labels_N{n}_G{args.groups}_{args.dist}",
@@ -225,7 +231,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from numpy_groupies_b200 import _abi, aggregate
+    from numpy_groupies_b200 import _abi, aggregate, aggregate_cuda
     from numpy_groupies_b200.distributed import aggregate_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -307,7 +313,7 @@ def main():
         "hbm_gbs_algorithmic": value * 12.0,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms,
-                     "algorithmic_bytes": alg_bytes, "kernel": "dominant accumulate kernel of the step (k_fast / k_cache / k_accumulate)"},
+                     "algorithmic_bytes": alg_bytes, "kernel": dominant_kernel(aggregate_cuda.last_regime())},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 
