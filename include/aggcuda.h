@@ -161,7 +161,8 @@ int64_t     agc_launch_count(void);
  *          decides (default), 2 always the cluster-partitioned table kernel, 3 always partial table + global RED
  *   key 1  CTAs per SM of the hot-key-cache kernel (1 | 2)
  *   key 2  kernel the probe picks for non-skewed labels (2 | 3, as key 0)
- *   key 3  per-mille of the groups the cluster kernel keeps on chip */
+ *   key 3  per-mille of the groups the cluster kernel keeps on chip
+ *   key 4  large tables, plain sums: one-word accumulators with carry forwarding (1, default) or two words (0) */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus

@@ -42,10 +42,10 @@ def last_regime():
     return _LAST["regime"]
 
 
-def tuning(large=-1, cache_ctas=-1, uniform=-1, cover=-1):
+def tuning(large=-1, cache_ctas=-1, uniform=-1, cover=-1, sum1=-1):
     """Kernel-selection knobs of libaggcuda (agc_tuning, include/aggcuda.h): for tests and A/B measurements."""
     lib = _abi.load()
-    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, uniform, cover)))
+    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, uniform, cover, sum1)))
 
 
 def _t():

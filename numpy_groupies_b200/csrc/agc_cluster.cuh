@@ -83,6 +83,10 @@ __device__ __forceinline__ unsigned long long spread8to16(unsigned v) {
 // labels are skewed or come in runs (the per-CTA hot-key cache wins there), else 0.
 // ---------------------------------------------------------------------------------------------
 constexpr int PROBE_SAMPLES = 32768;
+// A hash bucket holds 8 samples on average for uniform labels (max over 4096 buckets ~ 22).  One group with >= 0.1 % of
+// the elements adds >= 33: beyond that share its uncovered elements serialise on ONE L2 address (measured 1.5 ns per
+// RED: a 0.5 % group doubles the partial-table kernel's time, 1.5 % makes it 5x) and the hot-key cache wins.
+constexpr int PROBE_SKEW_COUNT = 40;
 template <class LT>
 __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int thresh) {
   __shared__ unsigned cnt[4096];
@@ -496,14 +500,16 @@ inline int cluster_plan(int mode, long long size, int* logc, int* slots, size_t*
 //   key 1  AGC_CACHE_CTAS CTAs per SM of k_cache (1 | 2)
 //   key 2  AGC_UNIFORM    kernel the probe picks for non-skewed labels: 2 k_cluster, 3 partial k_fast
 //   key 3  AGC_COVER      per-mille of the groups k_cluster keeps on chip (the rest are global REDs)
-enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_UNIFORM = 2, TUNE_COVER = 3, TUNE_COUNT = 4 };
-static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1};
+//   key 4  AGC_SUM1       large tables, plain sums: one-word accumulators with carry forwarding (1, default) or two-word (0)
+enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_UNIFORM = 2, TUNE_COVER = 3, TUNE_SUM1 = 4, TUNE_COUNT = 5 };
+static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1};
 inline void tuning_defaults() {
   if (g_tune[0] >= 0) return;
   const char* e;
   e = getenv("AGC_LARGE");      g_tune[TUNE_LARGE] = e ? atoi(e) : 1;       if (g_tune[TUNE_LARGE] < 0 || g_tune[TUNE_LARGE] > 3) g_tune[TUNE_LARGE] = 1;
   e = getenv("AGC_CACHE_CTAS"); g_tune[TUNE_CACHE_CTAS] = (e && atoi(e) == 1) ? 1 : 2;
   e = getenv("AGC_UNIFORM");    g_tune[TUNE_UNIFORM] = (e && atoi(e) == 2) ? 2 : 3;
+  e = getenv("AGC_SUM1");       g_tune[TUNE_SUM1] = (e && atoi(e) == 0) ? 0 : 1;
   e = getenv("AGC_COVER");      g_tune[TUNE_COVER] = e ? atoi(e) : 1000;    if (g_tune[TUNE_COVER] < 1 || g_tune[TUNE_COVER] > 1000) g_tune[TUNE_COVER] = 1000;
 }
 
@@ -583,8 +589,8 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   // launched and the one that was not chosen exits at once (no host synchronisation).
   int* choose = r->status + 4;
   if (probe) {
-    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SAMPLES / 50);
-    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SAMPLES / 50);
+    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SKEW_COUNT);
+    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SKEW_COUNT);
     AGC_COUNT_LAUNCH(1);
   }
   if (uniform_kernel == 2) {
@@ -604,11 +610,42 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     if (crc == 0) uniform_kernel = 3;                        // clusters unavailable: partial table instead
   }
   if (uniform_kernel == 3) {
-    // partial table: groups [0, cov) in shared memory, the rest global RED.  (Measured and rejected: CTA pairs that
-    // stream the same tiles and split the covered groups -- max at 10^5 groups 227 vs 285 Gelem/s.)
-    p.cov = (int)(cap1 / (words * 4));
+    // (partial) table in shared memory: groups [0, cov), the rest global RED.  Plain sums use the one-word format
+    // FM_SUM1 here (twice the coverage; its carries are REDs too, which is why it needs the probe's "not skewed").
+    // (Measured and rejected: CTA pairs that stream the same tiles and split the covered groups -- max at 10^5
+    // groups 227 vs 285 Gelem/s.)
+    const bool sum1 = mode == FM_SUM && g_tune[TUNE_SUM1] != 0;
+    // mean / var pass 1: one-word sums + a separate count pass over the labels (20 B/element, two kernels) beat the fused
+    // three-word table, whose coverage is a third and whose every uncovered element costs TWO RED packets
+    const bool split = mode == FM_SUMCNT && p.want_cnt && !want_b1 && g_tune[TUNE_SUM1] != 0 &&
+                       r->size * 4 > (long long)(cap1 / 12) * 5;   // the fused table would cover < 80 % of the groups
     p.choose = probe ? choose : nullptr; p.want = 0;
-    chunked(1, (size_t)p.cov * words * 4, false);
+    // one launch group of k_fast<M> with `w` words per group; `with_a`: the kernel reads the values
+    auto run_fast = [&](int m, int w, bool with_a, long long max_per_cta) {
+      const long long cov_max = (long long)(cap1 / (w * 4));
+      p.cov = (int)(cov_max < r->size ? cov_max : r->size);
+      const long long per_launch = (long long)sms * max_per_cta;
+      for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
+        p.n = r->n - off < per_launch ? r->n - off : per_launch;
+        p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
+        p.a = with_a ? (const float*)r->a + off : nullptr;
+        const size_t smem = (size_t)p.cov * w * 4;
+#define AGC_RUN_FAST(M)                                                                                          \
+        if (m == M) {                                                                                            \
+          if (i64) rc = with_a ? launch_fast<M, long long, true>(p, 1, smem, st, sms) : launch_fast<M, long long, false>(p, 1, smem, st, sms); \
+          else     rc = with_a ? launch_fast<M, int, true>(p, 1, smem, st, sms) : launch_fast<M, int, false>(p, 1, smem, st, sms);             \
+        }
+        AGC_RUN_FAST(FM_SUM) AGC_RUN_FAST(FM_SUMCNT) AGC_RUN_FAST(FM_MAX) AGC_RUN_FAST(FM_MIN) AGC_RUN_FAST(FM_LEN) AGC_RUN_FAST(FM_SUM1)
+#undef AGC_RUN_FAST
+      }
+      p.n = r->n; p.labels = r->index.labels; p.a = (const float*)r->a;
+    };
+    const long long no_limit = FAST_MAX_PER_CTA * 64;           // FM_SUM1 forwards its carries: no fixed-point headroom to respect
+    if (sum1) run_fast(FM_SUM1, 1, true, no_limit);
+    else if (split) {
+      run_fast(FM_SUM1, 1, true, no_limit);
+      if (rc >= 0) run_fast(FM_LEN, 1, nanskip, no_limit);      // u32 counts: < 2^32 elements per CTA
+    } else run_fast(mode, words, need_a, FAST_MAX_PER_CTA);
     if (rc < 0) return rc;
     p.cov = (int)r->size;
   }

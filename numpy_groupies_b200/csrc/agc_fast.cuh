@@ -23,7 +23,16 @@
 
 namespace agc {
 
-enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4 };
+enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4, FM_SUM1 = 5 };
+// FM_SUM1: ONE 32-bit word per group (k_fast only).  The word starts at 2^31 and takes q = x * 2^(FX1_F - E) with a
+// native ATOMS.ADD that returns the old value; a carry / borrow out of the word (the add crossed 0 or 2^32) is
+// forwarded at once as one exact f64 RED of +-2^32 units to the global table, so no bit is ever lost and there is
+// no per-launch headroom limit.  Half the shared memory per group: tables of up to 56 K groups fit one SM, and the
+// partial table of larger sizes covers twice as many groups -- at 10^5 groups that is the difference between 72 %
+// and ~48 % of the elements leaving the SM as RED packets.  The price is a 6-binade exact window (below it: bypass
+// RED), which is why the small-table kernels keep the two-word format.
+constexpr int FX1_F = 29;
+constexpr int FX1_WINDOW = 6;     // FX1_F - 23
 
 // A narrower window (FX_F = 31: |q| < 2^31, the high word then moves only on a carry, ~1.25 ATOMS per element)
 // was measured and rejected: the 0.4 % of rand() values that fall below an 8-binade window take the global RED
@@ -83,13 +92,15 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
+  constexpr bool IS_SUM = MODE == FM_SUM || MODE == FM_SUMCNT || MODE == FM_SUM1;
+  constexpr int FXF = MODE == FM_SUM1 ? FX1_F : FX_F, FXW = MODE == FM_SUM1 ? FX1_WINDOW : FX_WINDOW;
   const int rs = p.rshift;
   const int G = p.cov << rs;                       // table entries incl. replicas: entry = (g << rs) | (lane & (R-1))
   const int rsel = (threadIdx.x & 31) & ((1 << rs) - 1);
   unsigned* w0 = sw;            // sum.lo | key | count(FM_LEN)
   unsigned* w1 = sw + G;        // sum.hi
   unsigned* w2 = sw + 2 * G;    // count (FM_SUMCNT)
-  const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
+  const unsigned init0 = (MODE == FM_MAX || MODE == FM_SUM1) ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
   for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;   // G counts replicas
   if (threadIdx.x == 0) s_maxbits = 0u;
   __syncthreads();
@@ -102,7 +113,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
 
   // ---- reference exponent of this CTA: from its first tile ---------------------------------------
   unsigned lo_bits = 0, span_bits = 0; double scale = 1.0, inv_scale = 1.0;
-  if (MODE == FM_SUM || MODE == FM_SUMCNT) {
+  if (IS_SUM) {
     unsigned m = 0;
     if (v < nvec) {
       int4 av = ldg_stream16((const int4*)p.a + v);
@@ -120,13 +131,14 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     int eb = (int)(s_maxbits >> 23);            // biased exponent of the largest finite |value| seen
     if (eb == 0) eb = 127;                      // tile was all zero / non-finite: assume O(1) data
     eb += 1;                                    // values with biased exponent < eb convert
-    int lo_e = eb - FX_WINDOW; if (lo_e < 1) lo_e = 1;
+    int lo_e = eb - FXW; if (lo_e < 1) lo_e = 1;
     lo_bits = (unsigned)lo_e << 23;
     span_bits = (unsigned)(eb - lo_e) << 23;
-    // q = v * 2^(FX_F - (eb-127)) ; exact for in-window values
-    scale = __longlong_as_double((long long)(1023 + FX_F - (eb - 127)) << 52);
-    inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
+    // q = v * 2^(FXF - (eb-127)) ; exact for in-window values
+    scale = __longlong_as_double((long long)(1023 + FXF - (eb - 127)) << 52);
+    inv_scale = __longlong_as_double((long long)(1023 - FXF + (eb - 127)) << 52);
   }
+  const double hi_unit = inv_scale * 4294967296.0;        // FM_SUM1: what one carry out of the 32-bit word is worth
 
   // accumulate straight into the global tables (uncovered groups, ragged tail)
   auto direct_global = [&](long long g, float x) {
@@ -159,8 +171,15 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       if (p.square) x = x * x;
       unsigned ab = __float_as_uint(x) & 0x7fffffffu;
       if (ab - lo_bits < span_bits) {
-        long long q = __double2ll_rn((double)x * scale);
-        fx_add(w0 + gi, w1 + gi, q);
+        if (MODE == FM_SUM1) {
+          const int q = __double2int_rn((double)x * scale);                 // |q| < 2^29, exact
+          const unsigned old = atomicAdd(w0 + gi, (unsigned)q);
+          const int net = (q >> 31) + (int)(old + (unsigned)q < old);         // carry (+1) / borrow (-1) out of the word
+          if (net) atomicAdd(p.t.t0f + g, net > 0 ? hi_unit : -hi_unit);
+        } else {
+          long long q = __double2ll_rn((double)x * scale);
+          fx_add(w0 + gi, w1 + gi, q);
+        }
       } else if (ab != 0u) {
         atomicAdd(p.t.t0f + g, (double)x);          // out of window (huge / tiny / inf / NaN): exact f64 RED
       }
@@ -220,7 +239,8 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     } else {
       long long q = 0; unsigned long long c = 0;
       for (int r = 0; r < R; ++r) {
-        q += (long long)(((unsigned long long)w1[e0 + r] << 32) | w0[e0 + r]);     // <= 32 * 2^62 / 32: no overflow (FX_F headroom)
+        if (MODE == FM_SUM1) q += (long long)w0[e0 + r] - 0x80000000ll;              // residual around the 2^31 start value
+        else q += (long long)(((unsigned long long)w1[e0 + r] << 32) | w0[e0 + r]);  // <= 32 * 2^62 / 32: no overflow (FX_F headroom)
         if (MODE == FM_SUMCNT) c += w2[e0 + r];
       }
       if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
