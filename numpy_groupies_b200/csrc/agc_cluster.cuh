@@ -62,12 +62,15 @@ __device__ __forceinline__ uint2 ld_cluster_v2(unsigned addr) {
   uint2 v; asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v;
 }
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { __syncwarp(); asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+// (none of the cluster barriers uses `.aligned`: the classify step ends in data-dependent branches and an aligned
+// barrier issued by a warp the compiler has not reconverged is undefined -- it showed up as a sporadic
+// 'illegal instruction'.)
 // relaxed arrive: no MEMBAR.ALL.GPU (which would also wait for the prefetched global loads of the next tile).
 // The outbox stores are ordered by the __syncthreads() that precedes it: BAR.SYNC drains the CTA's pending STS
 // into the SM's shared memory, which is the only copy a peer's ld.shared::cluster can observe.
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { __syncwarp(); asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { __syncwarp(); asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 
 // 4 x 8-bit fields -> 4 x 16-bit fields
 __device__ __forceinline__ unsigned long long spread8to16(unsigned v) {

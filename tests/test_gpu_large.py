@@ -364,3 +364,19 @@ def test_one_word_sums_are_exact_for_dyadic_data(groups, signed):
         ac.tuning(large=1)
     exact = np.bincount(gidx, weights=k.astype(np.float64), minlength=groups) * 2.0 ** -24
     np.testing.assert_array_equal(got, exact)
+
+
+@pytest.mark.parametrize("func", ["cumsum", "cummax", "cummin"])
+def test_unsorted_n_to_n_multi_million(func):
+    """n > 2^22 unsorted labels: many tiles per radix pass and per segmented scan (bit-exact against the oracle)."""
+    rng = np.random.default_rng(71)
+    n, groups = (1 << 22) + 5, 50000
+    gidx = rng.integers(0, groups, n)
+    a = rng.integers(-2**31, 2**31, n)
+    got = aggregate(gidx, a, func=func, size=groups)
+    ref = oracle.aggregate(gidx, a, func=func, size=groups)
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
+    af = rng.standard_normal(n)
+    if func == "cumsum":
+        np.testing.assert_allclose(aggregate(gidx, af, func=func, size=groups), oracle.aggregate(gidx, af, func=func, size=groups), rtol=1e-9, atol=1e-9)
