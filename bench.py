@@ -208,8 +208,8 @@ def run_reference(args):
 
 
 def dominant_kernel(regime):
-    fam = {0: "k_accumulate (global tables)", 1: "k_fast (shared-memory table; partial table + global RED when size exceeds one SM)",
-           2: "k_cache (per-CTA hot-key cache + global RED)", 3: "k_cluster (cluster-partitioned table)", 4: "k_form3"}.get(regime // 10, "?")
+    fam = {0: "k_accumulate (global tables)", 1: "k_fast (shared-memory table; regime 15 = one-word carry-forwarding sums, partial table + global RED when size exceeds one SM)",
+           2: "k_cache (per-CTA hot-key cache + global RED)", 4: "k_form3", 5: "k_runs (segmented warp reduce)"}.get(regime // 10, "?")
     return f"accumulate stage of the step: {fam}, regime {regime}"
 
 

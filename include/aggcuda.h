@@ -158,11 +158,9 @@ float       agc_profile_last_ms(void);
 int64_t     agc_launch_count(void);
 /* kernel-selection knobs for A/B measurements and tests; value < 0 only reads.  Returns the (new) value.
  *   key 0  strategy for tables larger than one SM's shared memory: 0 hot-key cache, 1 on-device label probe
- *          decides (default), 2 always the cluster-partitioned table kernel, 3 always partial table + global RED
+ *          decides (default), 3 always partial table + global RED, 4 always the run kernel (segmented warp reduce)
  *   key 1  CTAs per SM of the hot-key-cache kernel (1 | 2)
- *   key 2  kernel the probe picks for non-skewed labels (2 | 3, as key 0)
- *   key 3  per-mille of the groups the cluster kernel keeps on chip
- *   key 4  large tables, plain sums: one-word accumulators with carry forwarding (1, default) or two words (0) */
+ *   key 2  large tables: one-word sums with carry forwarding and split mean (1, default) or fused tables (0) */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus

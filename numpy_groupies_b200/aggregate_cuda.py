@@ -38,14 +38,15 @@ _LAST = {"regime": 0, "probe": (0, 0, 0)}
 
 def last_regime():
     """Which accumulate kernel the last checked call used (status[3] of the C ABI): 0 general global-table
-    kernel, 10+mode k_fast, 20+mode k_cache, 30+mode k_cluster (mode: 0 sum, 1 sum+count, 2 max, 3 min, 4 len)."""
+    kernel, 10+mode k_fast, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs (mode: 0 sum, 1 sum+count, 2 max, 3 min,
+    4 len, 5 one-word sum)."""
     return _LAST["regime"]
 
 
-def tuning(large=-1, cache_ctas=-1, uniform=-1, cover=-1, sum1=-1):
+def tuning(large=-1, cache_ctas=-1, sum1=-1):
     """Kernel-selection knobs of libaggcuda (agc_tuning, include/aggcuda.h): for tests and A/B measurements."""
     lib = _abi.load()
-    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, uniform, cover, sum1)))
+    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1)))
 
 
 def _t():

@@ -1,0 +1,215 @@
+// agc_dispatch.cuh -- which accumulate kernel runs: the device-side label probe and try_fast_path().
+//
+//   table fits one SM's shared memory ............ k_fast (agc_fast.cuh), replicated when small
+//   Form 3 on the last axis ...................... k_form3 (agc_form3.cuh)
+//   larger tables (no host round trip: the probe writes status[4], every candidate kernel is launched and the ones
+//   that were not chosen return at once)
+//       labels in runs (sorted / contiguous) ..... k_runs  (agc_runs.cuh): segmented warp reduce
+//       skewed labels ............................ k_cache (agc_fast.cuh): per-CTA hot-key cache + global RED
+//       otherwise ................................ k_fast partial table + global RED; plain sums in the one-word
+//                                                  carry-forwarding format, mean / var as sum pass + count pass
+//   everything else .............................. k_accumulate (agc_generic.cuh)
+#pragma once
+#include "agc_fast.cuh"
+#include "agc_form3.cuh"
+#include "agc_runs.cuh"
+
+namespace agc {
+
+// ---------------------------------------------------------------------------------------------
+// label-distribution probe: 32 Ki strided samples -> (a) largest share of one hash bucket,
+// (b) share of positions whose right neighbour carries the same label.  status[4] = 1 when the
+// labels are skewed or come in runs (the per-CTA hot-key cache wins there), else 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int PROBE_SAMPLES = 32768;
+// A hash bucket holds 8 samples on average for uniform labels (max over 4096 buckets ~ 22).  One group with >= 0.1 % of
+// the elements adds >= 33: beyond that share its uncovered elements serialise on ONE L2 address (measured 1.5 ns per
+// RED: a 0.5 % group doubles the partial-table kernel's time, 1.5 % makes it 5x) and the hot-key cache wins.
+constexpr int PROBE_SKEW_COUNT = 40;
+template <class LT>
+__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int thresh) {
+  __shared__ unsigned cnt[4096];
+  __shared__ unsigned s_max, s_adj;
+  for (int i = threadIdx.x; i < 4096; i += 1024) cnt[i] = 0;
+  if (threadIdx.x == 0) { s_max = 0; s_adj = 0; }
+  __syncthreads();
+  const long long stride = n / PROBE_SAMPLES;          // >= 2 (callers guarantee n >= 65536)
+  unsigned adj = 0;
+#pragma unroll 8
+  for (int j = 0; j < PROBE_SAMPLES / 1024; ++j) {
+    const long long i = ((long long)j * 1024 + threadIdx.x) * stride;
+    const long long g = LabelVec<LT>::one(labels, i), gn = LabelVec<LT>::one(labels, i + 1);
+    atomicAdd(&cnt[((unsigned)g * 0x9E3779B1u) >> 20], 1u);
+    adj += g == gn;
+  }
+  adj = __reduce_add_sync(0xffffffffu, adj);
+  if ((threadIdx.x & 31) == 0 && adj) atomicAdd(&s_adj, adj);
+  __syncthreads();
+  unsigned m = 0;
+  for (int i = threadIdx.x; i < 4096; i += 1024) m = max(m, cnt[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(&s_max, m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // 2: labels come in runs (sorted / contiguous) -> segmented warp reduce; 1: skewed -> hot-key cache; 0: neither
+    status[4] = s_adj > PROBE_SAMPLES / 2 ? 2 : ((s_max > (unsigned)thresh || s_adj > PROBE_SAMPLES / 8) ? 1 : 0);
+    status[5] = (int)s_max;
+    status[6] = (int)s_adj;
+  }
+}
+
+// kernel-selection knobs (agc_tuning(); the environment gives the initial values)
+//   key 0  AGC_LARGE      strategy for tables larger than one SM's shared memory: 0 hot-key cache always, 1 the label
+//                         probe decides (default), 3 always partial k_fast, 4 always the run kernel
+//   key 1  AGC_CACHE_CTAS CTAs per SM of k_cache (1 | 2)
+//   key 2  AGC_SUM1       large tables: one-word sums with carry forwarding / split mean (1, default) or the fused
+//                         two- and three-word tables (0)
+enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_COUNT = 3 };
+static int g_tune[TUNE_COUNT] = {-1, -1, -1};
+inline void tuning_defaults() {
+  if (g_tune[0] >= 0) return;
+  const char* e;
+  e = getenv("AGC_LARGE");      g_tune[TUNE_LARGE] = e ? atoi(e) : 1;
+  if (g_tune[TUNE_LARGE] != 0 && g_tune[TUNE_LARGE] != 3 && g_tune[TUNE_LARGE] != 4) g_tune[TUNE_LARGE] = 1;
+  e = getenv("AGC_CACHE_CTAS"); g_tune[TUNE_CACHE_CTAS] = (e && atoi(e) == 1) ? 1 : 2;
+  e = getenv("AGC_SUM1");       g_tune[TUNE_SUM1] = (e && atoi(e) == 0) ? 0 : 1;
+}
+
+// returns 1 if it accumulated into the global tables (which it also initialises), 0 to fall back
+inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
+  if (r->index.form == AGC_FORM_AXIS) return try_form3_path(r, t, st, sms);
+  if (r->index.form != AGC_FORM_FLAT) return 0;
+  if (r->index.dtype != AGC_DT_I64 && r->index.dtype != AGC_DT_I32) return 0;
+  const int op = r->op;
+  const bool is_len = op == AGC_OP_LEN;
+  const bool nanskip = r->flags & AGC_F_NANSKIP;
+  if (!(op == AGC_OP_SUM || op == AGC_OP_SUMSQ || op == AGC_OP_MEAN || op == AGC_OP_MIN || op == AGC_OP_MAX || is_len || op == AGC_OP_VAR))
+    return 0;
+  const bool need_a = !is_len || nanskip;
+  if (need_a && (r->a == nullptr || r->a_dtype != AGC_DT_F32)) return 0;
+  if (r->n < (1 << 16) || r->size >= (1ll << 31)) return 0;
+  if (((uintptr_t)r->index.labels & 15) || (need_a && ((uintptr_t)r->a & 15))) return 0;
+  int mode;
+  const bool want_b1 = (op == AGC_OP_SUM || op == AGC_OP_SUMSQ) && (r->flags & AGC_F_NEED_TOUCHED);
+  if (is_len) mode = FM_LEN;
+  else if (op == AGC_OP_MAX) mode = FM_MAX;
+  else if (op == AGC_OP_MIN) mode = FM_MIN;
+  else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
+  else mode = FM_SUM;
+  const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
+  const size_t cap2 = 110 * 1024, cap1 = 227 * 1024 - 1024;
+  const size_t table = (size_t)r->size * words * 4;
+  const bool direct = table <= cap1;          // whole table privatised per CTA
+  tuning_defaults();
+  const int env_cache_ctas = g_tune[TUNE_CACHE_CTAS];
+  const int strategy = g_tune[TUNE_LARGE];
+  const int uniform_kernel = (strategy == 1 || strategy == 3) ? 3 : (strategy == 4 ? -1 : 0);   // 3: partial-table k_fast
+  const bool probe = strategy == 1;
+
+  FastParams p;
+  p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
+  p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
+  p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
+  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size;
+  AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
+  const bool i64 = r->index.dtype == AGC_DT_I64;
+  int rc = 0;
+
+#define AGC_FAST_LAUNCH(LAUNCHER, M, ...)                                                                        \
+  if (mode == M) {                                                                                               \
+    if (i64) rc = need_a ? LAUNCHER<M, long long, true>(__VA_ARGS__) : LAUNCHER<M, long long, false>(__VA_ARGS__); \
+    else     rc = need_a ? LAUNCHER<M, int, true>(__VA_ARGS__) : LAUNCHER<M, int, false>(__VA_ARGS__);             \
+  }
+#define AGC_FAST_ALL(LAUNCHER, ...)                                                                              \
+  AGC_FAST_LAUNCH(LAUNCHER, FM_SUM, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_SUMCNT, __VA_ARGS__)                 \
+  AGC_FAST_LAUNCH(LAUNCHER, FM_MAX, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_MIN, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_LEN, __VA_ARGS__)
+
+  // a CTA may take at most FAST_MAX_PER_CTA elements per launch (fixed-point / u32-count headroom): chunk N
+  auto chunked = [&](int ctas, size_t smem, bool cache) {
+    const long long per_launch = (long long)sms * ctas * FAST_MAX_PER_CTA;
+    const long long n_total = r->n;
+    for (long long off = 0; off < n_total && rc >= 0; off += per_launch) {
+      p.n = n_total - off < per_launch ? n_total - off : per_launch;
+      p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
+      p.a = need_a ? (const float*)r->a + off : nullptr;
+      if (cache) { AGC_FAST_ALL(launch_cache, p, ctas, smem, st, sms) }
+      else { AGC_FAST_ALL(launch_fast, p, ctas, smem, st, sms) }
+    }
+    p.n = r->n; p.labels = r->index.labels; p.a = (const float*)r->a;
+  };
+
+  if (direct) {
+    const int ctas = table <= cap2 ? 2 : 1;
+    if (ctas == 2) while (p.rshift < 5 && (table << (p.rshift + 1)) <= cap2) ++p.rshift;   // replicate small tables
+    chunked(ctas, table << p.rshift, false);
+    return rc;
+  }
+
+  // ---- table larger than one SM's shared memory ---------------------------------------------------------
+  // non-skewed labels: partial table + global RED (k_fast with cov < size);
+  // skewed labels / runs: per-CTA hot-key cache (k_cache).  The on-device label probe picks; both kernels are
+  // launched and the one that was not chosen exits at once (no host synchronisation).
+  int* choose = r->status + 4;
+  if (probe) {
+    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SKEW_COUNT);
+    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SKEW_COUNT);
+    AGC_COUNT_LAUNCH(1);
+  }
+  if (uniform_kernel == 3) {
+    // (partial) table in shared memory: groups [0, cov), the rest global RED.  Plain sums use the one-word format
+    // FM_SUM1 here (twice the coverage; its carries are REDs too, which is why it needs the probe's "not skewed").
+    // (Measured and rejected: CTA pairs that stream the same tiles and split the covered groups -- max at 10^5
+    // groups 227 vs 285 Gelem/s.)
+    const bool sum1 = mode == FM_SUM && g_tune[TUNE_SUM1] != 0;
+    // mean / var pass 1: one-word sums + a separate count pass over the labels (20 B/element, two kernels) beat the fused
+    // three-word table, whose coverage is a third and whose every uncovered element costs TWO RED packets
+    const bool split = mode == FM_SUMCNT && p.want_cnt && !want_b1 && g_tune[TUNE_SUM1] != 0 &&
+                       r->size * 4 > (long long)(cap1 / 12) * 5;   // the fused table would cover < 80 % of the groups
+    p.choose = probe ? choose : nullptr; p.want = 0;
+    // one launch group of k_fast<M> with `w` words per group; `with_a`: the kernel reads the values
+    auto run_fast = [&](int m, int w, bool with_a, long long max_per_cta) {
+      const long long cov_max = (long long)(cap1 / (w * 4));
+      p.cov = (int)(cov_max < r->size ? cov_max : r->size);
+      const long long per_launch = (long long)sms * max_per_cta;
+      for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
+        p.n = r->n - off < per_launch ? r->n - off : per_launch;
+        p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
+        p.a = with_a ? (const float*)r->a + off : nullptr;
+        const size_t smem = (size_t)p.cov * w * 4;
+#define AGC_RUN_FAST(M)                                                                                          \
+        if (m == M) {                                                                                            \
+          if (i64) rc = with_a ? launch_fast<M, long long, true>(p, 1, smem, st, sms) : launch_fast<M, long long, false>(p, 1, smem, st, sms); \
+          else     rc = with_a ? launch_fast<M, int, true>(p, 1, smem, st, sms) : launch_fast<M, int, false>(p, 1, smem, st, sms);             \
+        }
+        AGC_RUN_FAST(FM_SUM) AGC_RUN_FAST(FM_SUMCNT) AGC_RUN_FAST(FM_MAX) AGC_RUN_FAST(FM_MIN) AGC_RUN_FAST(FM_LEN) AGC_RUN_FAST(FM_SUM1)
+#undef AGC_RUN_FAST
+      }
+      p.n = r->n; p.labels = r->index.labels; p.a = (const float*)r->a;
+    };
+    const long long no_limit = FAST_MAX_PER_CTA * 64;           // FM_SUM1 forwards its carries: no fixed-point headroom to respect
+    if (sum1) run_fast(FM_SUM1, 1, true, no_limit);
+    else if (split) {
+      run_fast(FM_SUM1, 1, true, no_limit);
+      if (rc >= 0) run_fast(FM_LEN, 1, nanskip, no_limit);      // u32 counts: < 2^32 elements per CTA
+    } else run_fast(mode, words, need_a, FAST_MAX_PER_CTA);
+    if (rc < 0) return rc;
+    p.cov = (int)r->size;
+  }
+  if (strategy == 4 || probe) {                             // labels in runs: segmented warp reduce, no table at all
+    p.choose = probe ? choose : nullptr; p.want = 2; p.cov = (int)r->size;
+    AGC_FAST_ALL(launch_runs, p, st, sms)
+    if (rc < 0) return rc;
+  }
+  if (uniform_kernel == 0 || probe) {
+    const int ctas = env_cache_ctas;
+    const size_t budget = ctas == 2 ? cap2 : cap1;
+    p.nslots = (int)(budget / ((1 + words) * 4));
+    p.choose = probe ? choose : nullptr; p.want = 1;
+    chunked(ctas, (size_t)p.nslots * (1 + words) * 4, true);
+  }
+#undef AGC_FAST_ALL
+#undef AGC_FAST_LAUNCH
+  return rc < 0 ? rc : 1;
+}
+
+}  // namespace agc

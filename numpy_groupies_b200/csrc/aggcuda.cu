@@ -6,7 +6,7 @@
 #include "agc_common.cuh"
 #include "agc_generic.cuh"
 #include "agc_fast.cuh"
-#include "agc_cluster.cuh"
+#include "agc_dispatch.cuh"
 #include "agc_scan.cuh"
 
 namespace {

@@ -26,7 +26,7 @@ def timeit(fn, reps=5):
 for G in groups_list:
     lab = torch.randint(0, G, (n,), generator=g, device=dev)
     for func in ("sum", "mean", "max"):
-        configs = [("cache", dict(large=0)), ("partial2w", dict(large=3, sum1=0)), ("partial", dict(large=3, sum1=1)), ("cluster", dict(large=2, cover=1000))]
+        configs = [("cache", dict(large=0)), ("partial2w", dict(large=3, sum1=0)), ("partial", dict(large=3, sum1=1))]
         for name, kw in configs:
             ac.tuning(**kw)
             try:
@@ -36,4 +36,4 @@ for G in groups_list:
                                   "frac": round(n * 12 / ms * 1e-6 / peak, 3), "regime": ac.last_regime()}), flush=True)
             except Exception as ex:
                 print(json.dumps({"G": G, "func": func, "cfg": name, "error": str(ex)[:200]}), flush=True)
-        ac.tuning(large=1, cover=1000, sum1=1)
+        ac.tuning(large=1, sum1=1)

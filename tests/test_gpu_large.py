@@ -182,14 +182,15 @@ def test_full_size_properties_device_resident():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# cluster-partitioned table kernel (agc_cluster.cuh): tables between one SM's shared memory and eight SMs'
+# tables larger than one SM's shared memory: every kernel of agc_dispatch.cuh forced in turn
 # ---------------------------------------------------------------------------------------------------------
 CLUSTER_FUNCS = ["sum", "mean", "max", "min", "len", "sumofsquares", "var", "nansum", "nanmean", "nanmax", "nanlen"]
 
 
-@pytest.fixture(params=[2, 3], ids=["cluster", "partial"])
+@pytest.fixture(params=[0, 3, 4], ids=["cache", "partial", "runs"])
 def force_large(request):
-    """Force the kernel used for tables larger than one SM's shared memory: 2 = k_cluster, 3 = partial k_fast."""
+    """Force the kernel used for tables larger than one SM's shared memory: 0 = k_cache, 3 = partial k_fast,
+    4 = k_runs (segmented warp reduce; on random labels it degenerates into one RED per element)."""
     from numpy_groupies_b200 import aggregate_cuda as ac
     ac.tuning(large=request.param)
     yield ac, request.param
@@ -200,8 +201,8 @@ def force_large(request):
 @pytest.mark.parametrize("groups", [40000, 100000, 230000])
 @pytest.mark.parametrize("func", CLUSTER_FUNCS)
 def test_large_table_kernels_vs_oracle(func, groups, dist, force_large):
-    """Forced onto k_cluster / partial k_fast for every label distribution (the probe would send skewed / sorted
-    labels to the hot-key cache): same tolerances as the other f32 reductions; the regime word proves which ran."""
+    """Every large-table kernel forced onto every label distribution (the probe would route them apart): same
+    tolerances as the other f32 reductions; the regime word proves which kernel ran."""
     ac, strategy = force_large
     rng = np.random.default_rng(hash((func, groups, dist, "cl")) % 2**32)
     n = (1 << 21) + 3                                       # several phases per CTA + a ragged tail
@@ -216,34 +217,11 @@ def test_large_table_kernels_vs_oracle(func, groups, dist, force_large):
     assert got.dtype == ref.dtype and got.shape == ref.shape
     words = {"sum": 3, "nansum": 3, "sumofsquares": 3, "mean": 3, "nanmean": 3, "var": 3}.get(func, 1)   # fill=-1: sum+count
     if groups * words * 4 > 226 * 1024:                     # table larger than one SM's shared memory
-        assert regime // 10 == (3 if strategy == 2 else 1), regime
+        assert regime // 10 == {0: 2, 3: 1, 4: 5}[strategy], regime
     if func in ("max", "min", "nanmax", "len", "nanlen"):
         np.testing.assert_array_equal(got, ref)
     else:
         np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
-
-
-@pytest.mark.parametrize("cover", [300, 700])
-def test_cluster_kernel_partial_coverage(cover):
-    from numpy_groupies_b200 import aggregate_cuda as ac
-    rng = np.random.default_rng(78)
-    n, groups = (1 << 21) + 1, 100000
-    gidx = rng.integers(0, groups, n)
-    a = rng.standard_normal(n).astype(np.float32)
-    a[rng.random(n) < 0.05] = np.nan
-    try:
-        ac.tuning(large=2, cover=cover)
-        for func in ("sum", "nanmean", "max", "nanmin", "len", "nanlen"):
-            got = aggregate(gidx, a, func=func, size=groups)
-            assert ac.last_regime() // 10 == 3
-            with np.errstate(all="ignore"):
-                ref = oracle.aggregate(gidx, a, func=func, size=groups)
-            if func in ("max", "nanmin", "len", "nanlen"):
-                np.testing.assert_array_equal(got, ref)
-            else:
-                np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(ref)), equal_nan=True)
-    finally:
-        ac.tuning(large=1, cover=1000)
 
 
 def test_probe_routes_uniform_and_skewed_labels():
@@ -257,12 +235,12 @@ def test_probe_routes_uniform_and_skewed_labels():
         got = aggregate(gidx, a, func="sum", size=groups)
         seen[dist] = ac.last_regime()
         np.testing.assert_allclose(got, oracle.aggregate(gidx, a, func="sum", size=groups), rtol=1e-5)
-    assert seen["uniform"] in (10, 15, 30) and seen["zipf"] == 20 and seen["sorted"] == 20, seen
+    assert seen["uniform"] == 15 and seen["zipf"] == 20 and seen["sorted"] == 50, seen
 
 
 def test_large_table_kernels_full_size_agree():
-    """N = 2^28, 10^5 groups, device resident: many phases and several in-kernel merges; k_cluster and the partial
-    k_fast against k_cache (bit-exact for max / len; sums are exact fixed point up to the final f64 RED order)."""
+    """N = 2^28, 10^5 groups, device resident: the partial-table k_fast and k_runs against k_cache (bit-exact for
+    max / len; sums are exact fixed point / f64 partials up to the final f64 RED order)."""
     import torch
     from numpy_groupies_b200 import aggregate_cuda as ac
     n, groups = 1 << 28, 100000
@@ -271,19 +249,19 @@ def test_large_table_kernels_full_size_agree():
     a = torch.rand(n, generator=g, device="cuda")
     res = {}
     try:
-        for mode in (2, 3, 0):
+        for mode in (3, 4, 0):
             ac.tuning(large=mode)
             for func in ("sum", "mean", "max", "min", "len"):
                 res[mode, func] = aggregate(gidx, a, func=func, size=groups)
-                assert (ac.last_regime() // 10) == {2: 3, 3: 1, 0: 2}[mode], (mode, func, ac.last_regime())
+                assert (ac.last_regime() // 10) == {3: 1, 4: 5, 0: 2}[mode], (mode, func, ac.last_regime())
     finally:
         ac.tuning(large=1)
-    for mode in (2, 3):
+    for mode in (3, 4):
         for func in ("max", "min", "len"):
             assert torch.equal(res[mode, func], res[0, func]), (mode, func)
         for func in ("sum", "mean"):
             torch.testing.assert_close(res[mode, func], res[0, func], rtol=1e-6, atol=0)
-    assert int(res[2, "len"].sum()) == n
+    assert int(res[3, "len"].sum()) == n
 
 
 @pytest.mark.parametrize("func", ["sum", "mean", "max", "min", "nansum", "nanmean", "nanmax", "var", "sumofsquares"])
@@ -380,3 +358,27 @@ def test_unsorted_n_to_n_multi_million(func):
     af = rng.standard_normal(n)
     if func == "cumsum":
         np.testing.assert_allclose(aggregate(gidx, af, func=func, size=groups), oracle.aggregate(gidx, af, func=func, size=groups), rtol=1e-9, atol=1e-9)
+
+
+def test_sorted_labels_full_size_run_kernel():
+    """N = 2^28 sorted labels, 10^5 groups, device resident: the probe routes to k_runs (regime 50+mode); results agree
+    with the hot-key-cache kernel (bit-exact for max / len, 1e-6 for the f64-accumulated sums)."""
+    import torch
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    n, groups = 1 << 28, 100000
+    g = torch.Generator(device="cuda").manual_seed(100)
+    gidx = torch.sort(torch.randint(0, groups, (n,), generator=g, device="cuda")).values
+    a = torch.rand(n, generator=g, device="cuda")
+    res = {}
+    try:
+        for mode in (1, 0):
+            ac.tuning(large=mode)
+            for func in ("sum", "mean", "max", "len"):
+                res[mode, func] = aggregate(gidx, a, func=func, size=groups)
+                assert (ac.last_regime() // 10) == (5 if mode == 1 else 2), (mode, func, ac.last_regime())
+    finally:
+        ac.tuning(large=1)
+    for func in ("max", "len"):
+        assert torch.equal(res[1, func], res[0, func]), func
+    for func in ("sum", "mean"):
+        torch.testing.assert_close(res[1, func], res[0, func], rtol=1e-6, atol=0)
