@@ -193,4 +193,23 @@ __device__ __forceinline__ int4 ldg_stream16_ef(const void* p, unsigned long lon
   return r;
 }
 
+// RED with an L2 evict-last hint: keeps a large accumulator table (tens of MB) resident while GBs of input stream by
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_add_f64_hint(double* addr, double v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(addr), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_u64_hint(unsigned long long* addr, unsigned long long v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(addr), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_max_s64_hint(long long* addr, long long v, unsigned long long pol) {
+  asm volatile("red.global.max.L2::cache_hint.s64 [%0], %1, %2;" :: "l"(addr), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_min_s64_hint(long long* addr, long long v, unsigned long long pol) {
+  asm volatile("red.global.min.L2::cache_hint.s64 [%0], %1, %2;" :: "l"(addr), "l"(v), "l"(pol) : "memory");
+}
+
 }  // namespace agc

@@ -141,16 +141,18 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   const double hi_unit = inv_scale * 4294967296.0;        // FM_SUM1: what one carry out of the 32-bit word is worth
 
   // accumulate straight into the global tables (uncovered groups, ragged tail)
+  const unsigned long long pol = PARTIAL ? l2_evict_last_policy() : 0ull;
   auto direct_global = [&](long long g, float x) {
     const bool nan = x != x;
     if (LOAD_A && nan && nanskip) return;
-    if (MODE == FM_LEN) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull);
+    if (MODE == FM_LEN) { if (PARTIAL) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol); else atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); }
     else if (MODE == FM_MAX || MODE == FM_MIN) {
       const long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
-      if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64);
+      if (PARTIAL) { if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol); }
+      else { if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64); }
     } else {
       if (p.square) x = x * x;
-      if ((__float_as_uint(x) & 0x7fffffffu) != 0u) atomicAdd(p.t.t0f + g, (double)x);
+      if ((__float_as_uint(x) & 0x7fffffffu) != 0u) { if (PARTIAL) red_add_f64_hint(p.t.t0f + g, (double)x, pol); else atomicAdd(p.t.t0f + g, (double)x); }
       if (MODE == FM_SUMCNT) { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
     }
   };
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
     inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
   }
 
+  const unsigned long long pol = l2_evict_last_policy();       // misses: keep the global table in L2 while the input streams by
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
     if (LOAD_A && x != x && nanskip) return;
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
     if (t == 0u) { t = atomicCAS(tag + s, 0u, want); if (t == 0u) t = want; }
     const bool hit = t == want;
     if (MODE == FM_LEN) {
-      if (hit) atomicAdd(w0 + s, 1u); else atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull);
+      if (hit) atomicAdd(w0 + s, 1u); else red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol);
     } else if (MODE == FM_MAX || MODE == FM_MIN) {
       const bool nan = x != x;
       if (hit) {
@@ -319,18 +322,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
         if (MODE == FM_MAX) atomicMax((int*)w0 + s, k); else atomicMin((int*)w0 + s, k);
       } else {
         long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
-        if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64);
+        if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol);
       }
     } else {
       const unsigned ab = __float_as_uint(x) & 0x7fffffffu;
       if (hit && (ab - lo_bits < span_bits)) {
         fx_add(w0 + s, w1 + s, __double2ll_rn((double)x * scale));
       } else if (ab != 0u) {
-        atomicAdd(p.t.t0f + g, (double)x);                 // miss, or outside the exact window
+        red_add_f64_hint(p.t.t0f + g, (double)x, pol);     // miss, or outside the exact window
       }
       if (MODE == FM_SUMCNT) {
         if (hit) atomicAdd(w2 + s, 1u);
-        else { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
+        else { if (p.want_cnt) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol); if (p.want_b1) p.t.b1[g] = 1; }
       }
     }
   };

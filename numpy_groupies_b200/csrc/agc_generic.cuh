@@ -110,7 +110,7 @@ __global__ void k_means_inplace(Tables t, long long size) {
 // accumulate: one element -> its group's accumulators
 // ---------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, long long i, T v) {
+__device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, long long i, T v, unsigned long long pol) {
   const Tables& t = p.t;
   const bool nan = is_nan(v);
   if ((p.flags & AGC_F_NANSKIP) && nan) return;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
   if (p.pass == 2) {
     if (p.op == AGC_OP_VAR) {                       // sum (a - mean)^2 in f64, as the reference does
       double d = to_f64(v) - t.t0f[g];
-      atomicAdd(t.t2 + g, d * d);
+      red_add_f64_hint(t.t2 + g, d * d, pol);
     } else {                                        // arg*: first element equal to the group's extreme
       if (!nan && key_of(v) == t.t0i[g]) atomicMin(t.t1 + g, i + p.index_base);
     }
@@ -126,8 +126,8 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
   }
   switch (p.op) {
     case AGC_OP_SUM:
-      if (FL) atomicAdd(t.t0f + g, to_f64(v));
-      else atomicAdd((unsigned long long*)(t.t0i + g), (unsigned long long)v);
+      if (FL) red_add_f64_hint(t.t0f + g, to_f64(v), pol);
+      else red_add_u64_hint((unsigned long long*)(t.t0i + g), (unsigned long long)v, pol);
       if (p.flags & AGC_F_NEED_TOUCHED) t.b1[g] = 1;
       break;
     case AGC_OP_SUMSQ:
@@ -142,20 +142,20 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
       if (p.flags & AGC_F_NEED_TOUCHED) t.b1[g] = 1;
       break;
     case AGC_OP_LEN:
-      atomicAdd((unsigned long long*)(t.t1 + g), 1ull);
+      red_add_u64_hint((unsigned long long*)(t.t1 + g), 1ull, pol);
       break;
     case AGC_OP_MEAN: case AGC_OP_VAR:
-      atomicAdd(t.t0f + g, to_f64(v));
-      atomicAdd((unsigned long long*)(t.t1 + g), 1ull);
+      red_add_f64_hint(t.t0f + g, to_f64(v), pol);
+      red_add_u64_hint((unsigned long long*)(t.t1 + g), 1ull, pol);
       break;
     case AGC_OP_MAX: case AGC_OP_ARGMAX: {
       long long k = nan ? AGC_EMPTY_MIN /* = INT64_MAX: NaN beats everything */ : key_of(v);
-      atomicMax(t.t0i + g, k);
+      red_max_s64_hint(t.t0i + g, k, pol);
       if (!FL) t.b1[g] = 1;
       break; }
     case AGC_OP_MIN: case AGC_OP_ARGMIN: {
       long long k = nan ? AGC_EMPTY_MAX /* = INT64_MIN */ : key_of(v);
-      atomicMin(t.t0i + g, k);
+      red_min_s64_hint(t.t0i + g, k, pol);
       if (!FL) t.b1[g] = 1;
       break; }
     case AGC_OP_ANY: if (v != T(0)) t.b0[g] = 1; t.b1[g] = 1; break;       // NaN is truthy
@@ -171,12 +171,13 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
 template <class T>
 __global__ void __launch_bounds__(256) k_accumulate(const AccParams p) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned long long pol = l2_evict_last_policy();      // accumulator tables stay in L2 while the inputs stream by
   bool bad = false;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += stride) {
     long long g = p.ix.group(i);
     if (g < 0) { bad = true; continue; }
     T v = (p.op == AGC_OP_LEN && !(p.flags & AGC_F_NANSKIP)) ? T(0) : load_val<T>(p, i);
-    accumulate_one<T>(p, g, i, v);
+    accumulate_one<T>(p, g, i, v, pol);
   }
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
 }

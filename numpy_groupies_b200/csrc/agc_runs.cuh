@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_runs(const FastParams p) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool nanskip = p.flags & AGC_F_NANSKIP;
   const int ident = MODE == FM_MAX ? (int)0x80000000 : 0x7fffffff;          // "no element" key (a NaN pattern, never a real key)
+  const unsigned long long pol = l2_evict_last_policy();
   bool bad = false;
 
   // one element straight to the global tables
@@ -100,18 +101,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_runs(const FastParams p) {
     const bool last = uniform && (lane == 31 || nhead);
     if (last) {
       const long long gg = g[0];
-      if (MODE == FM_LEN) { if (c) atomicAdd((unsigned long long*)(p.t.t1 + gg), (unsigned long long)c); }
+      if (MODE == FM_LEN) { if (c) red_add_u64_hint((unsigned long long*)(p.t.t1 + gg), (unsigned long long)c, pol); }
       else if (MODE == FM_MAX || MODE == FM_MIN) {
         if (k != ident) {
           long long k64;
           if (MODE == FM_MAX) k64 = k == 0x7fffffff ? AGC_EMPTY_MIN : key_of((double)unkey_f32(k));
           else k64 = k == (int)0x80000000 ? AGC_EMPTY_MAX : key_of((double)unkey_f32(k));
-          if (MODE == FM_MAX) atomicMax(p.t.t0i + gg, k64); else atomicMin(p.t.t0i + gg, k64);
+          if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + gg, k64, pol); else red_min_s64_hint(p.t.t0i + gg, k64, pol);
         }
       } else {
-        if (s != 0.0) atomicAdd(p.t.t0f + gg, s);
+        if (s != 0.0) red_add_f64_hint(p.t.t0f + gg, s, pol);
         if (MODE == FM_SUMCNT && c) {
-          if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + gg), (unsigned long long)c);
+          if (p.want_cnt) red_add_u64_hint((unsigned long long*)(p.t.t1 + gg), (unsigned long long)c, pol);
           if (p.want_b1) p.t.b1[gg] = 1;
         }
       }
