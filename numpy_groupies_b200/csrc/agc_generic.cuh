@@ -120,7 +120,7 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
       double d = to_f64(v) - t.t0f[g];
       red_add_f64_hint(t.t2 + g, d * d, pol);
     } else {                                        // arg*: first element equal to the group's extreme
-      if (!nan && key_of(v) == t.t0i[g]) atomicMin(t.t1 + g, i + p.index_base);
+      if (!nan && key_of(v) == t.t0i[g] && i + p.index_base < t.t1[g]) atomicMin(t.t1 + g, i + p.index_base);   // stale read: only an extra atomic
     }
     return;
   }
@@ -128,18 +128,18 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
     case AGC_OP_SUM:
       if (FL) red_add_f64_hint(t.t0f + g, to_f64(v), pol);
       else red_add_u64_hint((unsigned long long*)(t.t0i + g), (unsigned long long)v, pol);
-      if (p.flags & AGC_F_NEED_TOUCHED) t.b1[g] = 1;
+      if ((p.flags & AGC_F_NEED_TOUCHED) && !t.b1[g]) t.b1[g] = 1;
       break;
     case AGC_OP_SUMSQ:
       if (FL) atomicAdd(t.t0f + g, to_f64((T)(v * v)));
       else atomicAdd((unsigned long long*)(t.t0i + g),
                      (unsigned long long)wrap_int((long long)((unsigned long long)v * (unsigned long long)v), p.a_dtype));
-      if (p.flags & AGC_F_NEED_TOUCHED) t.b1[g] = 1;
+      if ((p.flags & AGC_F_NEED_TOUCHED) && !t.b1[g]) t.b1[g] = 1;
       break;
     case AGC_OP_PROD:
       if (acc_is_float(p.op, p.a_dtype, p.out_dtype)) atomic_mul_f64(t.t0f + g, to_f64(v));
       else atomic_mul_u64((unsigned long long*)(t.t0i + g), (unsigned long long)v);
-      if (p.flags & AGC_F_NEED_TOUCHED) t.b1[g] = 1;
+      if ((p.flags & AGC_F_NEED_TOUCHED) && !t.b1[g]) t.b1[g] = 1;
       break;
     case AGC_OP_LEN:
       red_add_u64_hint((unsigned long long*)(t.t1 + g), 1ull, pol);
@@ -150,20 +150,22 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
       break;
     case AGC_OP_MAX: case AGC_OP_ARGMAX: {
       long long k = nan ? AGC_EMPTY_MIN /* = INT64_MAX: NaN beats everything */ : key_of(v);
-      red_max_s64_hint(t.t0i + g, k, pol);
-      if (!FL) t.b1[g] = 1;
+      // monotone update: a plain (possibly stale) read can only make us issue an unnecessary RED, never skip a needed
+      // one -- and with few groups almost every element fails the test, so the hot L2 addresses see no traffic
+      if (k > t.t0i[g]) red_max_s64_hint(t.t0i + g, k, pol);
+      if (!FL && !t.b1[g]) t.b1[g] = 1;
       break; }
     case AGC_OP_MIN: case AGC_OP_ARGMIN: {
       long long k = nan ? AGC_EMPTY_MAX /* = INT64_MIN */ : key_of(v);
-      red_min_s64_hint(t.t0i + g, k, pol);
-      if (!FL) t.b1[g] = 1;
+      if (k < t.t0i[g]) red_min_s64_hint(t.t0i + g, k, pol);
+      if (!FL && !t.b1[g]) t.b1[g] = 1;
       break; }
-    case AGC_OP_ANY: if (v != T(0)) t.b0[g] = 1; t.b1[g] = 1; break;       // NaN is truthy
-    case AGC_OP_ALL: if (v == T(0)) t.b0[g] = 0; t.b1[g] = 1; break;
-    case AGC_OP_ANYNAN: if (nan) t.b0[g] = 1; t.b1[g] = 1; break;
-    case AGC_OP_ALLNAN: if (!nan) t.b0[g] = 0; t.b1[g] = 1; break;
-    case AGC_OP_FIRST: atomicMin(t.t1 + g, i + p.index_base); break;
-    case AGC_OP_LAST: atomicMax(t.t1 + g, i + p.index_base); break;
+    case AGC_OP_ANY: if (v != T(0) && !t.b0[g]) t.b0[g] = 1; if (!t.b1[g]) t.b1[g] = 1; break;       // NaN is truthy; test-then-set keeps hot bytes read-only
+    case AGC_OP_ALL: if (v == T(0) && t.b0[g]) t.b0[g] = 0; if (!t.b1[g]) t.b1[g] = 1; break;
+    case AGC_OP_ANYNAN: if (nan && !t.b0[g]) t.b0[g] = 1; if (!t.b1[g]) t.b1[g] = 1; break;
+    case AGC_OP_ALLNAN: if (!nan && t.b0[g]) t.b0[g] = 0; if (!t.b1[g]) t.b1[g] = 1; break;
+    case AGC_OP_FIRST: if (i + p.index_base < t.t1[g]) atomicMin(t.t1 + g, i + p.index_base); break;
+    case AGC_OP_LAST: if (i + p.index_base > t.t1[g]) atomicMax(t.t1 + g, i + p.index_base); break;
     default: break;
   }
 }
@@ -173,7 +175,9 @@ __global__ void __launch_bounds__(256) k_accumulate(const AccParams p) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const unsigned long long pol = l2_evict_last_policy();      // accumulator tables stay in L2 while the inputs stream by
   bool bad = false;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += stride) {
+  const bool backwards = p.op == AGC_OP_LAST;                 // `last` walks from the end: after the first wave no element improves
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < p.n; j += stride) {
+    const long long i = backwards ? p.n - 1 - j : j;
     long long g = p.ix.group(i);
     if (g < 0) { bad = true; continue; }
     T v = (p.op == AGC_OP_LEN && !(p.flags & AGC_F_NANSKIP)) ? T(0) : load_val<T>(p, i);

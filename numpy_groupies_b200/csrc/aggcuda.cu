@@ -5,6 +5,7 @@
 #include <type_traits>
 #include "agc_common.cuh"
 #include "agc_generic.cuh"
+#include "agc_small.cuh"
 #include "agc_fast.cuh"
 #include "agc_dispatch.cuh"
 #include "agc_scan.cuh"
@@ -88,6 +89,16 @@ void launch_accumulate(const agc::AccParams& p, cudaStream_t st) {
   AGC_COUNT_LAUNCH(1), agc::k_accumulate<T><<<grid_for(p.n, 256, 16), 256, 0, st>>>(p);
 }
 void launch_accumulate_cls(const agc::AccParams& p, cudaStream_t st) {
+  if (p.n == 0) return;
+  if (!(p.flags & AGC_F_NO_FAST) && agc::small_path_ok(p.op, p.pass, p.n, p.size)) {       // few groups: per-CTA shared-memory copies
+    switch (p.a_dtype) {
+      case AGC_DT_F32: agc::launch_accumulate_small<float>(p, st, sm_count()); break;
+      case AGC_DT_F64: agc::launch_accumulate_small<double>(p, st, sm_count()); break;
+      case AGC_DT_U64: agc::launch_accumulate_small<unsigned long long>(p, st, sm_count()); break;
+      default: agc::launch_accumulate_small<long long>(p, st, sm_count()); break;
+    }
+    return;
+  }
   switch (p.a_dtype) {
     case AGC_DT_F32: launch_accumulate<float>(p, st); break;
     case AGC_DT_F64: launch_accumulate<double>(p, st); break;

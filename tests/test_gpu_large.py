@@ -382,3 +382,62 @@ def test_sorted_labels_full_size_run_kernel():
         assert torch.equal(res[1, func], res[0, func]), func
     for func in ("sum", "mean"):
         torch.testing.assert_close(res[1, func], res[0, func], rtol=1e-6, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# small tables on the general path (agc_small.cuh, regime 60): any dtype / Form, additive + multiplicative ops
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("groups", [7, 300, 4000, 12000])
+@pytest.mark.parametrize("func,dtype", [("sum", np.float64), ("nansum", np.float64), ("mean", np.float64), ("nanmean", np.float64),
+                                        ("var", np.float64), ("nanstd", np.float64), ("sumofsquares", np.float64), ("prod", np.float64),
+                                        ("sum", np.int64), ("sum", np.int16), ("sum", np.uint8), ("mean", np.int32), ("var", np.int64),
+                                        ("prod", np.int64), ("sumofsquares", np.int32), ("var", np.float32), ("prod", np.float32),
+                                        ("sum", np.bool_)])
+def test_small_table_general_kernel(func, dtype, groups):
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(hash((func, np.dtype(dtype).name, groups)) % 2**32)
+    n = (1 << 18) + 11
+    gidx = rng.integers(0, groups, n)
+    if np.dtype(dtype).kind == "f":
+        a = rng.standard_normal(n).astype(dtype)
+        if func == "prod":
+            a = (1 + a * 1e-3).astype(dtype)
+        if "nan" in func:
+            a[rng.random(n) < 0.1] = np.nan
+    elif np.dtype(dtype).kind == "b":
+        a = rng.random(n) < 0.3
+    elif func == "prod":
+        a = rng.integers(-2, 3, n).astype(dtype)
+    else:
+        info = np.iinfo(dtype)
+        lim = 30 if func == "sumofsquares" else 1000         # keep int32 sums of squares inside the dtype (overflow is garbage in the reference)
+        a = rng.integers(max(info.min, -lim), min(info.max, lim) + 1, n).astype(dtype)
+    got = aggregate(gidx, a, func=func, size=groups, fill_value=-1 if np.dtype(dtype).kind != "b" else 0, ddof=1) if "var" in func or "std" in func \
+        else aggregate(gidx, a, func=func, size=groups)
+    if np.dtype(dtype).kind != "f" or dtype != np.float32 or func == "prod":
+        assert ac.last_regime() == 60, ac.last_regime()
+    with np.errstate(all="ignore"):
+        ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=-1, ddof=1) if "var" in func or "std" in func \
+            else oracle.aggregate(gidx, a, func=func, size=groups)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    if got.dtype.kind == "f":
+        rtol = 1e-5 if dtype == np.float32 else 1e-12
+        np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * np.nanmax(np.abs(ref)), equal_nan=True)
+    else:
+        np.testing.assert_array_equal(got, ref)
+
+
+def test_small_table_general_kernel_forms_3_4():
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(83)
+    a = rng.standard_normal((300, 1000))                      # f64: general path
+    gidx = rng.integers(0, 9, 1000)
+    for func in ("sum", "mean", "var"):
+        got = aggregate(gidx, a, func=func, axis=1, size=9)
+        assert ac.last_regime() == 60
+        np.testing.assert_allclose(got, oracle.aggregate(gidx, a, func=func, axis=1, size=9), rtol=1e-12, atol=1e-12)
+    g2 = rng.integers(0, 40, (2, 1 << 18))
+    v = rng.integers(-50, 50, 1 << 18)
+    got = aggregate(g2, v, func="sum", size=(40, 40))
+    assert ac.last_regime() == 60
+    np.testing.assert_array_equal(got, oracle.aggregate(g2, v, func="sum", size=(40, 40)))
