@@ -110,7 +110,7 @@ class ClockSampler:
         self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -288,6 +288,38 @@ def main():
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3) * 1e-9
 
+    # ---- end-to-end through the public API with HOST (pinned) inputs, on every rank -------------------------
+    # each step: H2D of this rank's shard (labels + values) -> aggregate / aggregate_sharded -> D2H of the result
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e_log2n = min(args.log2n, 28 if world == 1 else 27)
+            ne = 1 << e2e_log2n
+            hl = labels[:ne].cpu().pin_memory()
+            ha = a[:ne].cpu().pin_memory()
+
+            def e2e_step():
+                if world > 1:                             # aggregate_sharded takes device shards: the H2D copy is the caller's
+                    r = aggregate_sharded(hl.to(device, non_blocking=True), ha.to(device, non_blocking=True), func=args.func, size=G)
+                else:
+                    r = aggregate(hl, ha, func=args.func, size=G)
+                return r.cpu()
+            e2e_step(); barrier()
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                e2e_step()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / reps], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
+            e2e = {"value": ne * world / dt * 1e-9, "unit": "Gelem/s", "h2d_bytes_per_step": ne * 12 * world, "d2h_bytes_per_step": G * 4 * world,
+                   "steps": reps, "n_per_gpu": ne, "note": "pinned host tensors -> aggregate() -> host result on every rank; PCIe-bound"}
+            del hl, ha
+        except Exception as e:                        # noqa: BLE001
+            e2e = {"value": None, "error": str(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -317,29 +349,9 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
     }
 
-    # ---- end-to-end through the public API with HOST (pinned) inputs ---------------------------------
-    if not args.no_e2e and world == 1:
-        try:
-            e2e_log2n = min(args.log2n, 28)
-            ne = 1 << e2e_log2n
-            hl = labels[:ne].cpu().pin_memory()
-            ha = a[:ne].cpu().pin_memory()
-            def e2e_step():
-                r = aggregate(hl, ha, func=args.func, size=G)
-                return r.cpu()
-            e2e_step(); torch.cuda.synchronize()
-            reps = 3
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                e2e_step()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / reps
-            line["e2e"] = {"value": ne / dt * 1e-9, "unit": "Gelem/s", "h2d_bytes_per_step": ne * 12, "d2h_bytes_per_step": G * 4,
-                           "steps": reps, "n": ne, "note": "pinned host tensors -> aggregate() -> host result; PCIe-bound"}
-        except Exception as e:                        # noqa: BLE001
-            line["e2e"] = {"value": None, "error": str(e)[:200]}
-    elif world > 1:
-        line["e2e"] = {"value": None, "note": "measured at N=1 only"}
+    # (the end-to-end leg ran on every rank before this point: see e2e_leg)
+    if e2e is not None:
+        line["e2e"] = e2e
 
     # ---- the other points of BASELINE config 2, same run -------------------------------------------------
     if not args.no_sweep and world == 1:
