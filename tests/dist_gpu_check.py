@@ -47,6 +47,25 @@ def main():
         else:
             np.testing.assert_array_equal(part, full, err_msg=func)
         checked += 1
+    # tables larger than one SM's shared memory: one-word sums, split mean, hot-key cache, run kernel under ACC_ONLY
+    groups2 = 120000
+    for dist_name in ("uniform", "sorted", "zipf"):
+        if dist_name == "uniform":
+            g2 = rng.integers(0, groups2, n)
+        elif dist_name == "sorted":
+            g2 = np.sort(rng.integers(0, groups2, n))
+        else:
+            w = 1.0 / np.arange(1, groups2 + 1) ** 1.1
+            g2 = rng.permutation(groups2)[np.minimum(np.searchsorted(np.cumsum(w) / w.sum(), rng.random(n)), groups2 - 1)]
+        for func in ("sum", "mean", "max", "len", "var"):
+            full = aggregate(torch.from_numpy(g2).cuda(), torch.from_numpy(a32).cuda(), func=func, size=groups2).cpu().numpy()
+            part = aggregate_sharded(torch.from_numpy(g2[lo:hi]).cuda(), torch.from_numpy(a32[lo:hi]).cuda(), func=func, size=groups2).cpu().numpy()
+            assert part.dtype == full.dtype and part.shape == full.shape, (func, part.dtype, full.dtype)
+            if func in ("max", "len"):
+                np.testing.assert_array_equal(part, full, err_msg=f"{func} {dist_name}")
+            else:
+                np.testing.assert_allclose(part, full, rtol=1e-5, atol=1e-6, err_msg=f"{func} {dist_name}")
+            checked += 1
     dist.barrier()
     if rank == 0:
         print(f"dist_gpu_check ok: {checked} functions, world={world}")
