@@ -187,11 +187,21 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
       p.n = r->n; p.labels = r->index.labels; p.a = (const float*)r->a;
     };
     const long long no_limit = FAST_MAX_PER_CTA * 64;           // FM_SUM1 forwards its carries: no fixed-point headroom to respect
+    // counts: 16-bit packed counters hold the whole table up to 113 K groups (k_len16), else the u32 partial table
+    const bool len16 = g_tune[TUNE_SUM1] != 0 && (size_t)((r->size + 1) / 2) * 4 <= cap1;
+    auto run_len = [&]() {
+      if (len16) {
+        p.cov = (int)r->size;
+        if (i64) rc = nanskip ? launch_len16<long long, true>(p, st, sms) : launch_len16<long long, false>(p, st, sms);
+        else     rc = nanskip ? launch_len16<int, true>(p, st, sms) : launch_len16<int, false>(p, st, sms);
+      } else run_fast(FM_LEN, 1, nanskip, no_limit);             // u32 counts: < 2^32 elements per CTA
+    };
     if (sum1) run_fast(FM_SUM1, 1, true, no_limit);
     else if (split) {
       run_fast(FM_SUM1, 1, true, no_limit);
-      if (rc >= 0) run_fast(FM_LEN, 1, nanskip, no_limit);      // u32 counts: < 2^32 elements per CTA
-    } else run_fast(mode, words, need_a, FAST_MAX_PER_CTA);
+      if (rc >= 0) run_len();
+    } else if (mode == FM_LEN) run_len();
+    else run_fast(mode, words, need_a, FAST_MAX_PER_CTA);
     if (rc < 0) return rc;
     p.cov = (int)r->size;
   }

@@ -254,6 +254,89 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_len16: counts with 16-bit counters, two per shared-memory word -- up to 113 K groups per SM.
+// `len`, and the count pass of the split mean / var on tables the one-word sum kernel also covers.
+// A counter uses 15 bits: the thread whose ATOMS.ADD returns a half equal to 0x7FFF (it made it 0x8000) takes
+// 0x8000 out of that half again and forwards 32768 to the global count.  Safety: the CTA runs a __syncthreads()
+// per tile of 16384 elements, so at most 16384 adds can land on a half between a detection and
+// its fix-up -- the half stays below 0x8000 + 1 + 16384 < 0xFFFF and never carries into its neighbour, and no second
+// thread can see 0x7FFF before the fix (that would need a wrap).  (The tile is 4 vectors per thread = 16384 adds.)
+// ---------------------------------------------------------------------------------------------
+template <class LT, bool LOAD_A>
+__global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
+  if (p.choose && *p.choose != p.want) return;
+  extern __shared__ unsigned sw[];
+  const int W = ((int)p.size + 1) >> 1;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) sw[i] = 0u;
+  __syncthreads();
+  const long long nvec = p.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  const unsigned long long pol = l2_evict_last_policy();
+  bool bad = false;
+  auto update = [&](long long g, float x) {
+    if ((unsigned long long)g >= (unsigned long long)p.size) { bad = true; return; }
+    if (LOAD_A && nanskip && x != x) return;
+    const int sh = ((int)g & 1) << 4;
+    const unsigned old = atomicAdd(sw + ((int)g >> 1), 1u << sh);
+    if (((old >> sh) & 0xffffu) == 0x7fffu) {
+      atomicSub(sw + ((int)g >> 1), 0x8000u << sh);
+      red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 0x8000ull, pol);
+    }
+  };
+  // block-uniform trip count: every thread reaches the barrier of every tile.  A tile is LEN16_U vectors per thread =
+  // 16384 elements (still < 0x7FFF adds between a detection and its fix-up), all loads of a tile are issued first.
+  constexpr int LEN16_U = 4;
+  for (long long vb = (long long)blockIdx.x * blockDim.x; vb < nvec; vb += stride * LEN16_U) {
+    long long g[LEN16_U][4]; float x[LEN16_U][4]; bool in[LEN16_U];
+#pragma unroll
+    for (int u = 0; u < LEN16_U; ++u) {
+      const long long v = vb + u * stride + threadIdx.x;
+      in[u] = v < nvec;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { g[u][k] = 0; x[u][k] = 0.f; }
+      if (in[u]) {
+        LabelVec<LT>::load(p.labels, v, g[u]);
+        if (LOAD_A) {
+          int4 av = ldg_stream16((const int4*)p.a + v);
+          x[u][0] = __int_as_float(av.x); x[u][1] = __int_as_float(av.y); x[u][2] = __int_as_float(av.z); x[u][3] = __int_as_float(av.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LEN16_U; ++u) {
+      if (!in[u]) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) update(g[u][k], x[u][k]);
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
+    const long long i = (nvec << 2) + threadIdx.x;
+    update(LabelVec<LT>::one(p.labels, i), LOAD_A ? p.a[i] : 0.f);
+  }
+  if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = 16;
+  __syncthreads();
+  for (int g = threadIdx.x; g < (int)p.size; g += blockDim.x) {
+    const unsigned c = (sw[g >> 1] >> ((g & 1) << 4)) & 0xffffu;
+    if (c) atomicAdd((unsigned long long*)(p.t.t1 + g), (unsigned long long)c);
+  }
+}
+template <class LT, bool LOAD_A>
+inline int launch_len16(const FastParams& p, cudaStream_t st, int sms) {
+  auto kern = k_len16<LT, LOAD_A>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
+    attr_done = true;
+  }
+  const size_t smem = (size_t)((p.size + 1) / 2) * 4;
+  AGC_COUNT_LAUNCH(1), kern<<<sms, FAST_THREADS, smem, st>>>(p);
+  return 1;
+}
+
 template <int MODE, class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
   if (p.choose && *p.choose != p.want) return;

@@ -441,3 +441,30 @@ def test_small_table_general_kernel_forms_3_4():
     got = aggregate(g2, v, func="sum", size=(40, 40))
     assert ac.last_regime() == 60
     np.testing.assert_array_equal(got, oracle.aggregate(g2, v, func="sum", size=(40, 40)))
+
+
+def test_len16_counter_overflow_is_forwarded_exactly():
+    """k_len16: two 16-bit counters per word; hot groups wrap the 15-bit range hundreds of times.  Neighbouring groups
+    (same word) must not disturb each other and nothing may be lost."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(97)
+    n, groups = (1 << 23) + 3, 100000
+    gidx = rng.integers(0, groups, n)
+    hot = rng.random(n)
+    gidx[hot < 0.45] = 4242            # even group: low half of its word
+    gidx[(hot >= 0.45) & (hot < 0.9)] = 4243   # odd neighbour: high half of the same word
+    a = rng.random(n, dtype=np.float32)
+    a[rng.random(n) < 0.05] = np.nan
+    try:
+        ac.tuning(large=3)
+        got = aggregate(gidx, a, func="len", size=groups)
+        assert ac.last_regime() == 16, ac.last_regime()
+        np.testing.assert_array_equal(got, np.bincount(gidx, minlength=groups))
+        got = aggregate(gidx, a, func="nanlen", size=groups)
+        np.testing.assert_array_equal(got, np.bincount(gidx[~np.isnan(a)], minlength=groups))
+        m = aggregate(gidx, a, func="nanmean", size=groups)
+        with np.errstate(all="ignore"):
+            ref = oracle.aggregate(gidx, a, func="nanmean", size=groups)
+        np.testing.assert_allclose(m, ref, rtol=1e-5, equal_nan=True)
+    finally:
+        ac.tuning(large=1)
