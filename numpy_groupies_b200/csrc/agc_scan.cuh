@@ -494,6 +494,38 @@ __device__ __forceinline__ A scan_from_raw(const ScanParams& p, unsigned long lo
   }
 }
 
+// Warp-cooperative transposed access for 8-byte elements: a warp owns 256 consecutive elements (2 KB).  Memory is
+// touched with fully coalesced 128-bit accesses (lane l -> chunk k*32 + l), the registers end up BLOCKED (thread t holds
+// elements 8t .. 8t+7) as the thread-local scan needs.  The 2 KB staging buffer per warp is XOR-swizzled
+// (chunk c lives at c ^ ((c >> 2) & 7)) so that both the striped and the blocked side are bank-conflict free.
+// Per-thread 64-byte loads reach the same DRAM bytes but cost 4x the L1 wavefronts (ncu: L1TEX 98 % busy).
+__device__ __forceinline__ void warp_load_blocked8(const void* src_warp, int4* wbuf, int lane, unsigned long long (&out)[SG_ITEMS]) {
+  const int4* q = (const int4*)src_warp;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int c = k * 32 + lane; wbuf[c ^ ((c >> 2) & 7)] = q[c]; }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * lane + j;
+    const int4 v = wbuf[c ^ ((c >> 2) & 7)];
+    out[2 * j] = ((unsigned long long)(unsigned)v.x) | ((unsigned long long)(unsigned)v.y << 32);
+    out[2 * j + 1] = ((unsigned long long)(unsigned)v.z) | ((unsigned long long)(unsigned)v.w << 32);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_store_blocked8(void* dst_warp, int4* wbuf, int lane, const unsigned long long (&in)[SG_ITEMS]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = 4 * lane + j;
+    wbuf[c ^ ((c >> 2) & 7)] = make_int4((int)(unsigned)in[2 * j], (int)(in[2 * j] >> 32), (int)(unsigned)in[2 * j + 1], (int)(in[2 * j + 1] >> 32));
+  }
+  __syncwarp();
+  int4* q = (int4*)dst_warp;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int c = k * 32 + lane; q[c] = wbuf[c ^ ((c >> 2) & 7)]; }
+  __syncwarp();
+}
+
 // Direct variant for flat int32/int64 labels that are already non-decreasing: no keys, no positions, no sort.
 // PHASE 0 reads (label, value) once for the tile aggregates and, on the way, verifies sortedness and label
 // bounds; PHASE 1 re-reads them, applies the carry and writes out[i] -- 40 B/element instead of the 64+ of the
@@ -533,13 +565,27 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
   const long long base = (long long)blockIdx.x * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
   A x[SG_ITEMS]; bool h[SG_ITEMS];
   long long g[SG_ITEMS];
-  load_labels8<LT>(p.labels, base, p.n, g);
+  __shared__ int4 s_stage[SG_THREADS / 32][128];            // 2 KB per warp: transposed 8-byte accesses
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const long long wbase = (long long)blockIdx.x * SG_TILE + (long long)wrp * (32 * SG_ITEMS);
+  const bool wfull = wbase + 32 * SG_ITEMS <= p.n;          // warp-uniform
+  const bool tr_lab = wfull && sizeof(LT) == 8;
+  const bool tr_val = wfull && dtype_bytes(p.a_dtype) == 8 && !((uintptr_t)p.a & 15);
+  if (tr_lab) {
+    unsigned long long gl[SG_ITEMS];
+    warp_load_blocked8((const long long*)p.labels + wbase, s_stage[wrp], lane, gl);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) g[k] = (long long)gl[k];
+  } else load_labels8<LT>(p.labels, base, p.n, g);
   long long prev = 0;
-  if (base > 0 && base - 1 < p.n) prev = sizeof(LT) == 8 ? ((const long long*)p.labels)[base - 1] : (long long)((const int*)p.labels)[base - 1];
+  const long long left = __shfl_up_sync(0xffffffffu, g[SG_ITEMS - 1], 1);      // the previous thread's last label
+  if (wfull && lane > 0) prev = left;
+  else if (base > 0 && base - 1 < p.n) prev = sizeof(LT) == 8 ? ((const long long*)p.labels)[base - 1] : (long long)((const int*)p.labels)[base - 1];
   bool tf = false; A tx = A(0); bool any = false, uns = false, bad = false;
   const bool vec = base + SG_ITEMS <= p.n && raw8_ok(p.a_dtype) && !((uintptr_t)p.a & 15);
   unsigned long long raw[SG_ITEMS];
-  if (vec) load_raw8(p.a, p.a_dtype, base, raw);
+  if (tr_val) warp_load_blocked8((const unsigned long long*)p.a + wbase, s_stage[wrp], lane, raw);
+  else if (vec) load_raw8(p.a, p.a_dtype, base, raw);
 #pragma unroll
   for (int k = 0; k < SG_ITEMS; ++k) {
     const long long i = base + k;
@@ -571,8 +617,12 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
   else if (have_c) { pre = cx; have = true; }
   bool open = have;
   // cumsum / cumprod into a 64-bit output of the accumulator's own class: results leave as 128-bit stores
-  const bool vst = (OP == SC_SUM || OP == SC_PROD) && base + SG_ITEMS <= p.n && !((uintptr_t)p.out & 15) &&
-                   (std::is_same<A, double>::value ? p.out_dtype == AGC_DT_F64 : (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64));
+  // integer running max / min keep the input dtype: for 64-bit integers the key IS the value (u64: sign bit flipped back)
+  const bool mm64 = (OP == SC_MAX || OP == SC_MIN) && !p.a_float && (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64);
+  const bool vst = base + SG_ITEMS <= p.n && !((uintptr_t)p.out & 15) &&
+                   (mm64 || ((OP == SC_SUM || OP == SC_PROD) &&
+                             (std::is_same<A, double>::value ? p.out_dtype == AGC_DT_F64 : (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64))));
+  const unsigned long long keyflip = (mm64 && p.a_u64) ? 0x8000000000000000ull : 0ull;
   A res[SG_ITEMS];
 #pragma unroll
   for (int k = 0; k < SG_ITEMS; ++k) {
@@ -583,12 +633,18 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
     res[k] = r;
     if (!vst) scan_store<A, OP>(p, i, r);
   }
-  if (vst) {
+  if (vst && wfull) {                                       // coalesced 128-bit stores through the warp's staging buffer
+    unsigned long long ob[SG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k)
+      ob[k] = std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)res[k]) : ((unsigned long long)(long long)res[k] ^ keyflip);
+    warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
+  } else if (vst) {
     int4* q = (int4*)((A*)p.out + base);
 #pragma unroll
     for (int k = 0; k < SG_ITEMS / 2; ++k) {
-      const long long b0 = std::is_same<A, double>::value ? __double_as_longlong((double)res[2 * k]) : (long long)res[2 * k];
-      const long long b1 = std::is_same<A, double>::value ? __double_as_longlong((double)res[2 * k + 1]) : (long long)res[2 * k + 1];
+      const long long b0 = std::is_same<A, double>::value ? __double_as_longlong((double)res[2 * k]) : (long long)((unsigned long long)(long long)res[2 * k] ^ keyflip);
+      const long long b1 = std::is_same<A, double>::value ? __double_as_longlong((double)res[2 * k + 1]) : (long long)((unsigned long long)(long long)res[2 * k + 1] ^ keyflip);
       q[k] = make_int4((int)(unsigned)b0, (int)(b0 >> 32), (int)(unsigned)b1, (int)(b1 >> 32));
     }
   }
