@@ -213,7 +213,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   if (uniform_kernel == 0 || probe) {
     const int ctas = env_cache_ctas;
     const size_t budget = ctas == 2 ? cap2 : cap1;
-    p.nslots = (int)(budget / ((1 + words) * 4));
+    p.nslots = (int)(budget / ((1 + words) * 4)) & ~1;          // even: slot s ^ 1 is the second way
     p.choose = probe ? choose : nullptr; p.want = 1;
     chunked(ctas, (size_t)p.nslots * (1 + words) * 4, true);
   }

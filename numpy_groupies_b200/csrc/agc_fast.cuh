@@ -391,10 +391,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
     if (LOAD_A && x != x && nanskip) return;
     if (MODE == FM_SUM || MODE == FM_SUMCNT) { if (p.square) x = x * x; }
     // ---- cache lookup ----
+    // 2-way: the key may live in slot s or in its neighbour s ^ 1 (two hot keys that hash together no longer fight:
+    // a permanent loser would send ALL its elements to one global address)
     const unsigned want = (unsigned)g + 1u;
-    const unsigned s = __umulhi((unsigned)g * 0x9E3779B1u, S);
+    unsigned s = __umulhi((unsigned)g * 0x9E3779B1u, S);
     unsigned t = tag[s];
     if (t == 0u) { t = atomicCAS(tag + s, 0u, want); if (t == 0u) t = want; }
+    if (t != want) {
+      const unsigned s2 = s ^ 1u;
+      unsigned t2 = tag[s2];
+      if (t2 == 0u) { t2 = atomicCAS(tag + s2, 0u, want); if (t2 == 0u) t2 = want; }
+      if (t2 == want) { s = s2; t = t2; }
+    }
     const bool hit = t == want;
     if (MODE == FM_LEN) {
       if (hit) atomicAdd(w0 + s, 1u); else red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol);
