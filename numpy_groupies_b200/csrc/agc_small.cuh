@@ -54,17 +54,14 @@ __global__ void __launch_bounds__(1024) k_accumulate_small(const AccParams p, in
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool nanskip = p.flags & AGC_F_NANSKIP;
   bool bad = false;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += stride) {
-    const long long g = p.ix.group(i);
-    if (g < 0) { bad = true; continue; }
-    const T v = load_val<T>(p, i);
-    if (nanskip && is_nan(v)) continue;
+  auto acc = [&](long long g, T v) {
+    if (nanskip && is_nan(v)) return;
     const int slot = ((int)g << rshift) | rsel;
     if (p.pass == 2) {                                    // var / std: sum (a - mean)^2, means already in T0
       const double d = to_f64(v) - p.t.t0f[g];
       atomicAdd(s0f + slot, d * d);
       atomicAdd(s1 + slot, 1u);
-      continue;
+      return;
     }
     switch (p.op) {
       case AGC_OP_SUM:
@@ -82,6 +79,38 @@ __global__ void __launch_bounds__(1024) k_accumulate_small(const AccParams p, in
         break;
     }
     atomicAdd(s1 + slot, 1u);
+  };
+  // Form 1, int64 labels, 8-byte values (f64 / int64 / uint64), 16-byte aligned: 128-bit streaming loads, two vectors
+  // (4 elements) per thread in flight -- the generic loop below costs a runtime dtype / Form switch per element
+  const bool fast8 = p.ix.ix.form == AGC_FORM_FLAT && p.ix.ix.dtype == AGC_DT_I64 && p.a != nullptr && sizeof(T) == 8 &&
+                     dtype_bytes(p.a_dtype) == 8 && !((uintptr_t)p.ix.ix.labels & 15) && !((uintptr_t)p.a & 15);
+  long long i0 = 0;
+  if (fast8) {
+    const long long nv = p.n >> 1;                        // vectors of 2 elements
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nv; v += 2 * stride) {
+      const long long v2 = v + stride;
+      const bool two = v2 < nv;
+      const int4 l0 = ldg_stream16((const int4*)p.ix.ix.labels + v), a0 = ldg_stream16((const int4*)p.a + v);
+      int4 l1 = make_int4(0, 0, 0, 0), a1 = l1;
+      if (two) { l1 = ldg_stream16((const int4*)p.ix.ix.labels + v2); a1 = ldg_stream16((const int4*)p.a + v2); }
+      const int4 ls[2] = {l0, l1}, as[2] = {a0, a1};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const long long g0 = ((long long)(unsigned)ls[u].x) | ((long long)ls[u].y << 32), g1 = ((long long)(unsigned)ls[u].z) | ((long long)ls[u].w << 32);
+        const long long b0 = ((long long)(unsigned)as[u].x) | ((long long)as[u].y << 32), b1 = ((long long)(unsigned)as[u].z) | ((long long)as[u].w << 32);
+        T x0, x1;
+        if (FL) { x0 = (T)__longlong_as_double(b0); x1 = (T)__longlong_as_double(b1); } else { x0 = (T)b0; x1 = (T)b1; }
+        if ((unsigned long long)g0 >= (unsigned long long)p.size) bad = true; else acc(g0, x0);
+        if ((unsigned long long)g1 >= (unsigned long long)p.size) bad = true; else acc(g1, x1);
+      }
+    }
+    i0 = nv << 1;                                         // odd tail element: generic loop
+  }
+  for (long long i = i0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const long long g = p.ix.group(i);
+    if (g < 0) { bad = true; continue; }
+    acc(g, load_val<T>(p, i));
   }
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.pass == 1) p.status[AGC_ST_REGIME] = 60;
