@@ -38,8 +38,8 @@ _LAST = {"regime": 0, "probe": (0, 0, 0)}
 
 def last_regime():
     """Which accumulate kernel the last checked call used (status[3] of the C ABI): 0 general global-table
-    kernel, 10+mode k_fast, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs (mode: 0 sum, 1 sum+count, 2 max, 3 min,
-    4 len, 5 one-word sum)."""
+    kernel, 10+mode k_fast (mode: 0 sum, 1 sum+count, 2 max, 3 min, 4 len, 5 one-word sum), 16 k_len16, 17 / 18
+    k_maxfilter max / min, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs, 60 k_accumulate_small."""
     return _LAST["regime"]
 
 

@@ -145,6 +145,13 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     return rc;
   }
 
+  // ---- max / min up to 113 K groups: the 16-bit filter kernel, whatever the label distribution -----------------
+  if ((mode == FM_MAX || mode == FM_MIN) && g_tune[TUNE_LARGE] == 1 && g_tune[TUNE_SUM1] != 0 && (size_t)((r->size + 1) / 2) * 4 <= cap1) {
+    if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long>(p, st, sms) : launch_maxfilter<true, int>(p, st, sms);
+    else rc = i64 ? launch_maxfilter<false, long long>(p, st, sms) : launch_maxfilter<false, int>(p, st, sms);
+    return rc;
+  }
+
   // ---- table larger than one SM's shared memory ---------------------------------------------------------
   // non-skewed labels: partial table + global RED (k_fast with cov < size);
   // skewed labels / runs: per-CTA hot-key cache (k_cache).  The on-device label probe picks; both kernels are

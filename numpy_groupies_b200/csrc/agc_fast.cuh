@@ -337,6 +337,77 @@ inline int launch_len16(const FastParams& p, cudaStream_t st, int sms) {
   return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_maxfilter: max / min for tables of up to 113 K groups -- a 16-bit FILTER per group in shared memory.
+// top[g] holds the upper 16 bits of the order-preserving key of some element of group g this CTA has already sent to
+// the global table.  An element whose upper 16 bits are smaller cannot be the maximum and is dropped after one LDS;
+// otherwise it is sent (exact 64-bit key, RED.MAX) and, if larger, recorded with a plain 16-bit store.  No shared
+// atomics: a lost store only makes the filter weaker, never wrong, because every stored value comes from an element
+// that did reach the global table.  A CTA sees ~70 elements of a group at 10^5 groups and N = 2^30, so about 7 % of
+// the elements still pass (record highs + ties in the upper 16 bits); the rest never leave the SM, for uniform,
+// skewed and sorted labels alike.  NaN "wins" in the reference: it maps to the top code 0xFFFF, after which the
+// group's filter rejects everything.  min uses the complemented key.  (ncu: half of the stall samples wait for the
+// global loads -- one CTA of 1024 threads per SM; a register double-buffered prefetch spilled and was slower.)
+// ---------------------------------------------------------------------------------------------
+template <bool ISMAX, class LT>
+__global__ void __launch_bounds__(FAST_THREADS, 1) k_maxfilter(const FastParams p) {
+  if (p.choose && *p.choose != p.want) return;
+  extern __shared__ unsigned sw[];
+  unsigned short* top = (unsigned short*)sw;
+  const int W = ((int)p.size + 1) >> 1;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) sw[i] = 0u;
+  __syncthreads();
+  const long long nvec = p.n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  const unsigned long long pol = l2_evict_last_policy();
+  bool bad = false;
+  auto update = [&](long long g, float x) {
+    if ((unsigned long long)g >= (unsigned long long)p.size) { bad = true; return; }
+    const bool nan = x != x;
+    if (nan && nanskip) return;
+    const int k32 = nan ? (ISMAX ? 0x7fffffff : (int)0x80000000) : key32_of(x);              // NaN wins
+    const unsigned u = ISMAX ? ((unsigned)k32 ^ 0x80000000u) : ~((unsigned)k32 ^ 0x80000000u);  // larger u = better
+    const unsigned t = u >> 16;
+    const unsigned cur = top[g];
+    if (t < cur || cur == 0xffffu) return;
+    const long long k64 = nan ? (ISMAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
+    if (ISMAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol);
+    if (t > cur) top[g] = (unsigned short)t;
+  };
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += 2 * stride) {
+    long long g[2][4]; int4 av[2];
+    const bool two = v + stride < nvec;
+    LabelVec<LT>::load(p.labels, v, g[0]);
+    av[0] = ldg_stream16((const int4*)p.a + v);
+    if (two) { LabelVec<LT>::load(p.labels, v + stride, g[1]); av[1] = ldg_stream16((const int4*)p.a + v + stride); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      update(g[u][0], __int_as_float(av[u].x)); update(g[u][1], __int_as_float(av[u].y));
+      update(g[u][2], __int_as_float(av[u].z)); update(g[u][3], __int_as_float(av[u].w));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
+    const long long i = (nvec << 2) + threadIdx.x;
+    update(LabelVec<LT>::one(p.labels, i), p.a[i]);
+  }
+  if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = ISMAX ? 17 : 18;
+}
+template <bool ISMAX, class LT>
+inline int launch_maxfilter(const FastParams& p, cudaStream_t st, int sms) {
+  auto kern = k_maxfilter<ISMAX, LT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
+    attr_done = true;
+  }
+  const size_t smem = (size_t)((p.size + 1) / 2) * 4;
+  AGC_COUNT_LAUNCH(1), kern<<<sms, FAST_THREADS, smem, st>>>(p);
+  return 1;
+}
+
 template <int MODE, class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
   if (p.choose && *p.choose != p.want) return;

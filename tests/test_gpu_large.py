@@ -375,7 +375,8 @@ def test_sorted_labels_full_size_run_kernel():
             ac.tuning(large=mode)
             for func in ("sum", "mean", "max", "len"):
                 res[mode, func] = aggregate(gidx, a, func=func, size=groups)
-                assert (ac.last_regime() // 10) == (5 if mode == 1 else 2), (mode, func, ac.last_regime())
+                want = 2 if mode == 0 else (1 if func == "max" else 5)       # default: max -> filter kernel (17), rest -> k_runs
+                assert (ac.last_regime() // 10) == want, (mode, func, ac.last_regime())
     finally:
         ac.tuning(large=1)
     for func in ("max", "len"):
@@ -468,3 +469,25 @@ def test_len16_counter_overflow_is_forwarded_exactly():
         np.testing.assert_allclose(m, ref, rtol=1e-5, equal_nan=True)
     finally:
         ac.tuning(large=1)
+
+
+@pytest.mark.parametrize("dist", ["uniform", "zipf", "sorted"])
+@pytest.mark.parametrize("func", ["max", "min", "nanmax", "nanmin"])
+def test_max_min_filter_kernel(func, dist):
+    """56 K < size <= 113 K groups: k_maxfilter (regime 17 / 18), bit-exact incl. NaN propagation, +-inf, -0.0 vs 0.0
+    ordering aside, all-NaN groups and never-touched groups."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(hash((func, dist, "flt")) % 2**32)
+    n, groups = (1 << 21) + 2, 100000
+    gidx = _labels(rng, n, groups - 100, dist)                 # the last 100 groups stay empty -> fill_value
+    a = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n)).astype(np.float32)
+    a[rng.random(n) < 0.05] = np.nan
+    a[::5003] = np.inf
+    a[7::5003] = -np.inf
+    a[gidx == gidx[0]] = np.nan                               # one group with nothing but NaN
+    got = aggregate(gidx, a, func=func, size=groups, fill_value=-5)
+    assert ac.last_regime() == (17 if "max" in func else 18), ac.last_regime()
+    with np.errstate(all="ignore"):
+        ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=-5)
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
