@@ -97,5 +97,17 @@ def last_error():
     return load().agc_last_error().decode()
 
 
+_DT_CACHE = {}
+
+
 def dtype_code(np_dtype):
-    return DT[np.dtype(np_dtype).name]
+    # np.dtype(...).name is surprisingly slow (string assembly on every access): cache by the dtype object itself
+    try:
+        return _DT_CACHE[np_dtype]
+    except (KeyError, TypeError):
+        code = DT[np.dtype(np_dtype).name]
+        try:
+            _DT_CACHE[np_dtype] = code
+        except TypeError:
+            pass
+        return code

@@ -57,11 +57,33 @@ def _t():
     return _torch
 
 
+_cuda_ok = False
+
+
 def _require_cuda():
+    global _cuda_ok
     torch = _t()
-    if not torch.cuda.is_available():
-        raise RuntimeError("aggregate_cuda needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if not _cuda_ok:                                        # is_available() costs several microseconds per call: ask once
+        if not torch.cuda.is_available():
+            raise RuntimeError("aggregate_cuda needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _cuda_ok = True
     return torch
+
+
+_NAME = {}
+
+
+def _dtname(dt):
+    """np.dtype(dt).name through a cache (the property assembles the string on every access)."""
+    try:
+        return _NAME[dt]
+    except (KeyError, TypeError):
+        name = np.dtype(dt).name
+        try:
+            _NAME[dt] = name
+        except TypeError:
+            pass
+        return name
 
 
 # numpy dtype name -> torch dtype used to *carry* the bytes (unsigned types travel as same-width signed)
@@ -87,8 +109,16 @@ def _is_tensor(x):
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
+_TORCH_NP = {}
+
+
 def _tensor_np_dtype(t):
-    return np.dtype(str(t.dtype).split(".")[-1])
+    try:
+        return _TORCH_NP[t.dtype]
+    except KeyError:
+        dt = np.dtype(str(t.dtype).split(".")[-1])
+        _TORCH_NP[t.dtype] = dt
+        return dt
 
 
 def _upload(arr, device):
@@ -107,7 +137,7 @@ def _from_tensor(t):
 
 def _empty(n, dtype, device):
     torch = _t()
-    return _Dev(torch.empty(int(n), dtype=getattr(torch, _CARRIER[np.dtype(dtype).name]), device=device), dtype)
+    return _Dev(torch.empty(int(n), dtype=getattr(torch, _CARRIER[_dtname(dtype)]), device=device), dtype)
 
 
 def _download(dev, shape=None):
@@ -119,8 +149,9 @@ def _download(dev, shape=None):
 
 def _as_user_tensor(dev):
     torch = _t()
-    if dev.dtype.name in _SIGNED_VIEW and hasattr(torch, dev.dtype.name):
-        return dev.t.view(getattr(torch, dev.dtype.name))
+    nm = _dtname(dev.dtype)
+    if nm in _SIGNED_VIEW and hasattr(torch, nm):
+        return dev.t.view(getattr(torch, nm))
     return dev.t
 
 
@@ -297,7 +328,7 @@ def _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, kwargs, r
         flags |= _abi.F_ASSUME_SORTED
     if not c.fast:
         flags |= _abi.F_NO_FAST
-    if out_dtype == np.dtype(object) or out_dtype.name not in _abi.DT and out_dtype.name != "float16":
+    if out_dtype == np.dtype(object) or _dtname(out_dtype) not in _abi.DT and _dtname(out_dtype) != "float16":
         raise NotImplementedError(f"output dtype {out_dtype} is not supported by aggregate_cuda")
     if base in _N_TO_N and plan.ndim_idx > 1 and int(np.prod(plan.out_shape, dtype=np.int64)) != plan.n:
         # N->N result cannot be reshaped to the group grid (reference: reshape error, aggregate_numpy.py:366)
@@ -321,7 +352,11 @@ def _device_of(c):
 
 
 def _stream_ptr(device):
-    return _t().cuda.current_stream(device).cuda_stream
+    torch = _t()
+    try:                                                    # raw handle, ~10x cheaper than building a Stream object
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except Exception:                                       # noqa: BLE001
+        return torch.cuda.current_stream(device).cuda_stream
 
 
 def _labels_on_device(c, device):
@@ -382,7 +417,7 @@ def _values_on_device(c, device):
     a = c.a
     if _is_tensor(a):
         dev = _from_tensor(a)
-        if dev.dtype.name in _COMPUTE_AS:
+        if _dtname(dev.dtype) in _COMPUTE_AS:
             dev = _Dev(dev.t.to(_t().float32), np.float32)
         dev.t = dev.t.reshape(-1)
         return dev
@@ -402,12 +437,12 @@ def _run_device(c):
     base = c.base
     n_out = plan.n if base in _N_TO_N else plan.flat_size
     out_np_dtype = c.out_dtype
-    compute_out = np.dtype(_COMPUTE_AS.get(out_np_dtype.name, out_np_dtype))
+    compute_out = np.dtype(_COMPUTE_AS.get(_dtname(out_np_dtype), out_np_dtype))
 
     req = _abi.Request()
     req.op = _abi.OP[base]
     req.flags = c.flags
-    a_dt = np.dtype(_COMPUTE_AS.get(c.a_dtype.name, c.a_dtype))
+    a_dt = np.dtype(_COMPUTE_AS.get(_dtname(c.a_dtype), c.a_dtype))
     req.a_dtype = _abi.dtype_code(a_dt)
     req.out_dtype = _abi.dtype_code(compute_out)
     if vals is None:

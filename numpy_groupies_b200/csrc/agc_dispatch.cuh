@@ -21,22 +21,22 @@ namespace agc {
 // (b) share of positions whose right neighbour carries the same label.  status[4] = 1 when the
 // labels are skewed or come in runs (the per-CTA hot-key cache wins there), else 0.
 // ---------------------------------------------------------------------------------------------
-constexpr int PROBE_SAMPLES = 32768;
+constexpr int PROBE_SAMPLES = 32768;                // at n >= 2^23; fewer for smaller inputs (n / 256, at least 4096)
 // A hash bucket holds 8 samples on average for uniform labels (max over 4096 buckets ~ 22).  One group with >= 0.1 % of
 // the elements adds >= 33: beyond that share its uncovered elements serialise on ONE L2 address (measured 1.5 ns per
 // RED: a 0.5 % group doubles the partial-table kernel's time, 1.5 % makes it 5x) and the hot-key cache wins.
 constexpr int PROBE_SKEW_COUNT = 40;
 template <class LT>
-__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int thresh) {
+__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int samples, int thresh) {
   __shared__ unsigned cnt[4096];
   __shared__ unsigned s_max, s_adj;
   for (int i = threadIdx.x; i < 4096; i += 1024) cnt[i] = 0;
   if (threadIdx.x == 0) { s_max = 0; s_adj = 0; }
   __syncthreads();
-  const long long stride = n / PROBE_SAMPLES;          // >= 2 (callers guarantee n >= 65536)
+  const long long stride = n / samples;                // >= 2 (callers guarantee n >= 65536 and samples <= n / 16)
   unsigned adj = 0;
 #pragma unroll 8
-  for (int j = 0; j < PROBE_SAMPLES / 1024; ++j) {
+  for (int j = 0; j < samples / 1024; ++j) {
     const long long i = ((long long)j * 1024 + threadIdx.x) * stride;
     const long long g = LabelVec<LT>::one(labels, i), gn = LabelVec<LT>::one(labels, i + 1);
     atomicAdd(&cnt[((unsigned)g * 0x9E3779B1u) >> 20], 1u);
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
   __syncthreads();
   if (threadIdx.x == 0) {
     // 2: labels come in runs (sorted / contiguous) -> segmented warp reduce; 1: skewed -> hot-key cache; 0: neither
-    status[4] = s_adj > PROBE_SAMPLES / 2 ? 2 : ((s_max > (unsigned)thresh || s_adj > PROBE_SAMPLES / 8) ? 1 : 0);
+    status[4] = s_adj > (unsigned)samples / 2 ? 2 : ((s_max > (unsigned)thresh || s_adj > (unsigned)samples / 8) ? 1 : 0);
     status[5] = (int)s_max;
     status[6] = (int)s_adj;
   }
@@ -158,8 +158,13 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   // launched and the one that was not chosen exits at once (no host synchronisation).
   int* choose = r->status + 4;
   if (probe) {
-    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SKEW_COUNT);
-    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, PROBE_SKEW_COUNT);
+    // the probe is one CTA and costs ~1 us per 1024 samples: scale it with the input (a hot group hurts in proportion to n)
+    long long samples = r->n / 256;
+    samples = samples < 4096 ? 4096 : (samples > PROBE_SAMPLES ? PROBE_SAMPLES : samples);
+    samples &= ~1023ll;
+    const int thresh = (int)(12 + samples * (PROBE_SKEW_COUNT - 12) / PROBE_SAMPLES);       // 40 at 32 Ki samples (0.1 % share), 15 at 4 Ki (0.35 %)
+    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
+    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
     AGC_COUNT_LAUNCH(1);
   }
   if (uniform_kernel == 3) {
