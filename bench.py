@@ -195,10 +195,12 @@ def run_reference(args):
         oracle.aggregate(labels, a, func=args.func, size=args.groups)
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt * 1e-9
-    line = {"impl": "reference", "metric": f"aggregate {args.func} throughput", "value": val, "unit": "Gelem/s",
+    cfg = workload_config(args)
+    cfg["reference_sample"] = f"each timed step aggregates N=2^{args.cpu_log2n} elements drawn like the workload's (bounded CPU sample)"
+    line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": "Gelem/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n_override=n),
+            "config": cfg,
             "cpu_baseline": {"value": val, "unit": "Gelem/s", "cores": 1, "kind": "port",
                              "sample": f"each step = N=2^{args.cpu_log2n} elements of the workload; numpy restatement of "
                                        f"aggregate_numpy (single-threaded by construction, host has {os.cpu_count()} cores)"},
@@ -211,6 +213,10 @@ def dominant_kernel(regime):
     fam = {0: "k_accumulate (global tables)", 1: "k_fast (shared-memory table; regime 15 = one-word carry-forwarding sums, partial table + global RED when size exceeds one SM)",
            2: "k_cache (per-CTA hot-key cache + global RED)", 4: "k_form3", 5: "k_runs (segmented warp reduce)"}.get(regime // 10, "?")
     return f"accumulate stage of the step: {fam}, regime {regime}"
+
+
+def metric_name(args):
+    return f"aggregate {args.func} throughput (Form 1, N=2^{args.log2n}/GPU f32, int64 labels, {args.groups} groups {args.dist})"
 
 
 def workload_config(args, n_override=None):
@@ -338,7 +344,7 @@ def main():
         except Exception:
             traffic = None
     line = {
-        "metric": f"aggregate {args.func} throughput (Form 1, N=2^{args.log2n}/GPU f32, int64 labels, {G} groups {args.dist})",
+        "metric": metric_name(args),
         "value": value, "unit": "Gelem/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),

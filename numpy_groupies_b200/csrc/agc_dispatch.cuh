@@ -145,10 +145,22 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     return rc;
   }
 
-  // ---- max / min up to 113 K groups: the 16-bit filter kernel, whatever the label distribution -----------------
+  // ---- max / min up to 113 K groups: the 16-bit filter kernel for uniform and skewed labels alike; labels in runs
+  //      (the probe says 2) go to the segmented warp reduce, which streams them at HBM rate ------------------------
   if ((mode == FM_MAX || mode == FM_MIN) && g_tune[TUNE_LARGE] == 1 && g_tune[TUNE_SUM1] != 0 && (size_t)((r->size + 1) / 2) * 4 <= cap1) {
+    long long samples = r->n / 256;
+    samples = samples < 4096 ? 4096 : (samples > PROBE_SAMPLES ? PROBE_SAMPLES : samples);
+    samples &= ~1023ll;
+    const int thresh = (int)(12 + samples * (PROBE_SKEW_COUNT - 12) / PROBE_SAMPLES);
+    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
+    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
+    AGC_COUNT_LAUNCH(1);
+    p.choose = r->status + 4; p.want = 0;
     if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long>(p, st, sms) : launch_maxfilter<true, int>(p, st, sms);
     else rc = i64 ? launch_maxfilter<false, long long>(p, st, sms) : launch_maxfilter<false, int>(p, st, sms);
+    if (rc < 0) return rc;
+    p.want = 2;
+    AGC_FAST_ALL(launch_runs, p, st, sms)
     return rc;
   }
 

@@ -351,7 +351,7 @@ inline int launch_len16(const FastParams& p, cudaStream_t st, int sms) {
 // ---------------------------------------------------------------------------------------------
 template <bool ISMAX, class LT>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_maxfilter(const FastParams p) {
-  if (p.choose && *p.choose != p.want) return;
+  if (p.choose && *p.choose == 2) return;                   // labels in runs: k_runs streams them at HBM rate
   extern __shared__ unsigned sw[];
   unsigned short* top = (unsigned short*)sw;
   const int W = ((int)p.size + 1) >> 1;
