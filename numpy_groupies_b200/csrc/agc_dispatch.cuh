@@ -64,8 +64,13 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
 //   key 1  AGC_CACHE_CTAS CTAs per SM of k_cache (1 | 2)
 //   key 2  AGC_SUM1       large tables: one-word sums with carry forwarding / split mean (1, default) or the fused
 //                         two- and three-word tables (0)
-enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_COUNT = 3 };
-static int g_tune[TUNE_COUNT] = {-1, -1, -1};
+//   key 3  AGC_SMEM1      bytes of dynamic shared memory one CTA per SM may use for its table.  Default 199552: with
+//                         more than 196 KB of shared memory per SM the L1 keeps 28 KB, which caps the global loads
+//                         in flight -- a streaming kernel then reaches 350-370 instead of 500-590 Gelem/s
+//                         (measured cliff between 196 000 and 200 000 B of table, profiles/r01d_smem_carveout_cliff.jsonl)
+//   key 4  AGC_SMEM2      the same for kernels that run two CTAs per SM (default 99200)
+enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_COUNT = 5 };
+static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1};
 inline void tuning_defaults() {
   if (g_tune[0] >= 0) return;
   const char* e;
@@ -73,7 +78,11 @@ inline void tuning_defaults() {
   if (g_tune[TUNE_LARGE] != 0 && g_tune[TUNE_LARGE] != 3 && g_tune[TUNE_LARGE] != 4) g_tune[TUNE_LARGE] = 1;
   e = getenv("AGC_CACHE_CTAS"); g_tune[TUNE_CACHE_CTAS] = (e && atoi(e) == 1) ? 1 : 2;
   e = getenv("AGC_SUM1");       g_tune[TUNE_SUM1] = (e && atoi(e) == 0) ? 0 : 1;
+  e = getenv("AGC_SMEM1");      g_tune[TUNE_SMEM1] = e ? atoi(e) : 199552;
+  e = getenv("AGC_SMEM2");      g_tune[TUNE_SMEM2] = e ? atoi(e) : 99200;
 }
+inline size_t smem_cap1() { int v = g_tune[TUNE_SMEM1]; return (size_t)(v < 16384 ? 16384 : (v > 227 * 1024 - 1024 ? 227 * 1024 - 1024 : v)); }
+inline size_t smem_cap2() { int v = g_tune[TUNE_SMEM2]; return (size_t)(v < 8192 ? 8192 : (v > 110 * 1024 ? 110 * 1024 : v)); }
 
 // returns 1 if it accumulated into the global tables (which it also initialises), 0 to fall back
 inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
@@ -97,10 +106,10 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
   else mode = FM_SUM;
   const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
-  const size_t cap2 = 110 * 1024, cap1 = 227 * 1024 - 1024;
+  tuning_defaults();
+  const size_t cap2 = smem_cap2(), cap1 = smem_cap1();
   const size_t table = (size_t)r->size * words * 4;
   const bool direct = table <= cap1;          // whole table privatised per CTA
-  tuning_defaults();
   const int env_cache_ctas = g_tune[TUNE_CACHE_CTAS];
   const int strategy = g_tune[TUNE_LARGE];
   const int uniform_kernel = (strategy == 1 || strategy == 3) ? 3 : (strategy == 4 ? -1 : 0);   // 3: partial-table k_fast
@@ -147,7 +156,18 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
 
   // ---- max / min up to 113 K groups: the 16-bit filter kernel for uniform and skewed labels alike; labels in runs
   //      (the probe says 2) go to the segmented warp reduce, which streams them at HBM rate ------------------------
-  if ((mode == FM_MAX || mode == FM_MIN) && g_tune[TUNE_LARGE] == 1 && g_tune[TUNE_SUM1] != 0 && (size_t)((r->size + 1) / 2) * 4 <= cap1) {
+  // Partial tables: how many groups get a shared-memory slot of `bpg` bytes.  Up to 195 KB the SM keeps 60 KB of L1 and the
+  // kernel streams at HBM rate; the last 31 KB of shared memory cost a third of the load bandwidth, which only pays when
+  // the kernel is bound by the REDs of its uncovered groups anyway (measured: profiles/r01d_smem_carveout_cliff.jsonl).
+  const size_t cap_max = 227 * 1024 - 1024;
+  auto pick_cov = [&](size_t bpg_num, size_t bpg_den) -> long long {      // bytes per group = bpg_num / bpg_den
+    const long long fast = (long long)(cap1 * bpg_den / bpg_num), big = (long long)(cap_max * bpg_den / bpg_num);
+    if (r->size <= fast) return r->size;
+    if (cap1 >= cap_max || (double)(r->size - fast) <= 0.15 * (double)r->size) return fast & ~1ll;
+    return (r->size < big ? r->size : big) & ~1ll;
+  };
+  const long long cov16 = pick_cov(2, 1);                    // groups a table of 16-bit entries covers
+  if ((mode == FM_MAX || mode == FM_MIN) && g_tune[TUNE_LARGE] == 1 && g_tune[TUNE_SUM1] != 0 && r->size <= 8 * (long long)(cap_max / 2)) {
     long long samples = r->n / 256;
     samples = samples < 4096 ? 4096 : (samples > PROBE_SAMPLES ? PROBE_SAMPLES : samples);
     samples &= ~1023ll;
@@ -156,10 +176,15 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
     AGC_COUNT_LAUNCH(1);
     p.choose = r->status + 4; p.want = 0;
-    if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long>(p, st, sms) : launch_maxfilter<true, int>(p, st, sms);
-    else rc = i64 ? launch_maxfilter<false, long long>(p, st, sms) : launch_maxfilter<false, int>(p, st, sms);
+    p.cov = (int)(r->size < cov16 ? r->size : cov16);        // groups beyond the filter table always pass (one RED each)
+    if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long, false>(p, st, sms) : launch_maxfilter<true, int, false>(p, st, sms);
+    else rc = i64 ? launch_maxfilter<false, long long, false>(p, st, sms) : launch_maxfilter<false, int, false>(p, st, sms);
     if (rc < 0) return rc;
-    p.want = 2;
+    p.want = 1;                                              // skewed labels: the same kernel with the exact test on ties
+    if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long, true>(p, st, sms) : launch_maxfilter<true, int, true>(p, st, sms);
+    else rc = i64 ? launch_maxfilter<false, long long, true>(p, st, sms) : launch_maxfilter<false, int, true>(p, st, sms);
+    if (rc < 0) return rc;
+    p.want = 2; p.cov = (int)r->size;
     AGC_FAST_ALL(launch_runs, p, st, sms)
     return rc;
   }
@@ -192,8 +217,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     p.choose = probe ? choose : nullptr; p.want = 0;
     // one launch group of k_fast<M> with `w` words per group; `with_a`: the kernel reads the values
     auto run_fast = [&](int m, int w, bool with_a, long long max_per_cta) {
-      const long long cov_max = (long long)(cap1 / (w * 4));
-      p.cov = (int)(cov_max < r->size ? cov_max : r->size);
+      p.cov = (int)pick_cov((size_t)w * 4, 1);
       const long long per_launch = (long long)sms * max_per_cta;
       for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
         p.n = r->n - off < per_launch ? r->n - off : per_launch;
@@ -212,10 +236,10 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     };
     const long long no_limit = FAST_MAX_PER_CTA * 64;           // FM_SUM1 forwards its carries: no fixed-point headroom to respect
     // counts: 16-bit packed counters hold the whole table up to 113 K groups (k_len16), else the u32 partial table
-    const bool len16 = g_tune[TUNE_SUM1] != 0 && (size_t)((r->size + 1) / 2) * 4 <= cap1;
+    const bool len16 = g_tune[TUNE_SUM1] != 0 && r->size <= 8 * (long long)(cap_max / 2);
     auto run_len = [&]() {
       if (len16) {
-        p.cov = (int)r->size;
+        p.cov = (int)(r->size < cov16 ? r->size : cov16);
         if (i64) rc = nanskip ? launch_len16<long long, true>(p, st, sms) : launch_len16<long long, false>(p, st, sms);
         else     rc = nanskip ? launch_len16<int, true>(p, st, sms) : launch_len16<int, false>(p, st, sms);
       } else run_fast(FM_LEN, 1, nanskip, no_limit);             // u32 counts: < 2^32 elements per CTA
@@ -236,7 +260,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   }
   if (uniform_kernel == 0 || probe) {
     const int ctas = env_cache_ctas;
-    const size_t budget = ctas == 2 ? cap2 : cap1;
+    const size_t budget = ctas == 2 ? 110 * 1024 : cap_max;     // the cache is RED-bound on its misses: capacity beats L1 here
     p.nslots = (int)(budget / ((1 + words) * 4)) & ~1;          // even: slot s ^ 1 is the second way
     p.choose = probe ? choose : nullptr; p.want = 1;
     chunked(ctas, (size_t)p.nslots * (1 + words) * 4, true);

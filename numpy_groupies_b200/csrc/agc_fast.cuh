@@ -267,7 +267,7 @@ template <class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
   if (p.choose && *p.choose != p.want) return;
   extern __shared__ unsigned sw[];
-  const int W = ((int)p.size + 1) >> 1;
+  const int W = (p.cov + 1) >> 1;                              // groups [0, cov) have a counter, the rest go straight to the global table
   for (int i = threadIdx.x; i < W; i += blockDim.x) sw[i] = 0u;
   __syncthreads();
   const long long nvec = p.n >> 2;
@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
   auto update = [&](long long g, float x) {
     if ((unsigned long long)g >= (unsigned long long)p.size) { bad = true; return; }
     if (LOAD_A && nanskip && x != x) return;
+    if (g >= p.cov) { red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol); return; }
     const int sh = ((int)g & 1) << 4;
     const unsigned old = atomicAdd(sw + ((int)g >> 1), 1u << sh);
     if (((old >> sh) & 0xffffu) == 0x7fffu) {
@@ -286,31 +287,53 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
     }
   };
   // block-uniform trip count: every thread reaches the barrier of every tile.  A tile is LEN16_U vectors per thread =
-  // 16384 elements (still < 0x7FFF adds between a detection and its fix-up), all loads of a tile are issued first.
-  constexpr int LEN16_U = 4;
-  for (long long vb = (long long)blockIdx.x * blockDim.x; vb < nvec; vb += stride * LEN16_U) {
-    long long g[LEN16_U][4]; float x[LEN16_U][4]; bool in[LEN16_U];
+  // 8192 elements (< 0x7FFF adds between a detection and its fix-up).  Two register stages: the loads of tile t+1 are
+  // issued before tile t is counted, so the barrier does not expose the load latency.
+  constexpr int LEN16_U = 2;
+  struct Stage { long long g[LEN16_U][4]; float x[LEN16_U][4]; bool in[LEN16_U]; };
+  auto load_tile = [&](Stage& s, long long vb) {
 #pragma unroll
     for (int u = 0; u < LEN16_U; ++u) {
       const long long v = vb + u * stride + threadIdx.x;
-      in[u] = v < nvec;
+      s.in[u] = v < nvec;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { g[u][k] = 0; x[u][k] = 0.f; }
-      if (in[u]) {
-        LabelVec<LT>::load(p.labels, v, g[u]);
+      for (int k = 0; k < 4; ++k) { s.g[u][k] = 0; s.x[u][k] = 0.f; }
+      if (s.in[u]) {
+        LabelVec<LT>::load(p.labels, v, s.g[u]);
         if (LOAD_A) {
           int4 av = ldg_stream16((const int4*)p.a + v);
-          x[u][0] = __int_as_float(av.x); x[u][1] = __int_as_float(av.y); x[u][2] = __int_as_float(av.z); x[u][3] = __int_as_float(av.w);
+          s.x[u][0] = __int_as_float(av.x); s.x[u][1] = __int_as_float(av.y); s.x[u][2] = __int_as_float(av.z); s.x[u][3] = __int_as_float(av.w);
         }
       }
     }
+  };
+  auto count_tile = [&](const Stage& s) {
 #pragma unroll
     for (int u = 0; u < LEN16_U; ++u) {
-      if (!in[u]) continue;
+      if (!s.in[u]) continue;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) update(g[u][k], x[u][k]);
+      for (int k = 0; k < 4; ++k) update(s.g[u][k], s.x[u][k]);
     }
     __syncthreads();
+  };
+  {
+    const long long tile = stride * LEN16_U;
+    long long vb = (long long)blockIdx.x * blockDim.x;
+    if (vb < nvec) {
+      Stage sa, sb;
+      load_tile(sa, vb);
+      for (;;) {
+        const bool more1 = vb + tile < nvec;
+        if (more1) load_tile(sb, vb + tile);
+        count_tile(sa);
+        if (!more1) break;
+        const bool more2 = vb + 2 * tile < nvec;
+        if (more2) load_tile(sa, vb + 2 * tile);
+        count_tile(sb);
+        if (!more2) break;
+        vb += 2 * tile;
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
     const long long i = (nvec << 2) + threadIdx.x;
@@ -319,7 +342,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = 16;
   __syncthreads();
-  for (int g = threadIdx.x; g < (int)p.size; g += blockDim.x) {
+  for (int g = threadIdx.x; g < p.cov; g += blockDim.x) {
     const unsigned c = (sw[g >> 1] >> ((g & 1) << 4)) & 0xffffu;
     if (c) atomicAdd((unsigned long long*)(p.t.t1 + g), (unsigned long long)c);
   }
@@ -332,7 +355,7 @@ inline int launch_len16(const FastParams& p, cudaStream_t st, int sms) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
     attr_done = true;
   }
-  const size_t smem = (size_t)((p.size + 1) / 2) * 4;
+  const size_t smem = (size_t)((p.cov + 1) / 2) * 4;
   AGC_COUNT_LAUNCH(1), kern<<<sms, FAST_THREADS, smem, st>>>(p);
   return 1;
 }
@@ -349,12 +372,12 @@ inline int launch_len16(const FastParams& p, cudaStream_t st, int sms) {
 // group's filter rejects everything.  min uses the complemented key.  (ncu: half of the stall samples wait for the
 // global loads -- one CTA of 1024 threads per SM; a register double-buffered prefetch spilled and was slower.)
 // ---------------------------------------------------------------------------------------------
-template <bool ISMAX, class LT>
+template <bool ISMAX, class LT, bool TIE>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_maxfilter(const FastParams p) {
-  if (p.choose && *p.choose == 2) return;                   // labels in runs: k_runs streams them at HBM rate
+  if (p.choose && *p.choose != p.want) return;              // 0: uniform labels (TIE = false), 1: skewed (TIE = true); runs go to k_runs
   extern __shared__ unsigned sw[];
   unsigned short* top = (unsigned short*)sw;
-  const int W = ((int)p.size + 1) >> 1;
+  const int W = (p.cov + 1) >> 1;                              // groups [0, cov) have a filter word, the rest always pass
   for (int i = threadIdx.x; i < W; i += blockDim.x) sw[i] = 0u;
   __syncthreads();
   const long long nvec = p.n >> 2;
@@ -369,23 +392,62 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_maxfilter(const FastParams 
     const int k32 = nan ? (ISMAX ? 0x7fffffff : (int)0x80000000) : key32_of(x);              // NaN wins
     const unsigned u = ISMAX ? ((unsigned)k32 ^ 0x80000000u) : ~((unsigned)k32 ^ 0x80000000u);  // larger u = better
     const unsigned t = u >> 16;
-    const unsigned cur = top[g];
+    const unsigned cur = g < p.cov ? (unsigned)top[g] : 0u;
     if (t < cur || cur == 0xffffu) return;
     const long long k64 = nan ? (ISMAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
     if (ISMAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol);
-    if (t > cur) top[g] = (unsigned short)t;
+    if (t > cur && g < p.cov) top[g] = (unsigned short)t;
   };
+  // A batch of MF_B elements reads its filter words first (independent LDS, one latency) and decides afterwards: a
+  // filter word that an earlier element of the same batch has just raised is read stale, which only lets a few more
+  // elements through.  (One element at a time, the chain LDS -> compare -> STS of 8 elements was a third of the
+  // kernel's stall samples.)
+  constexpr int MF_B = 8;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += 2 * stride) {
     long long g[2][4]; int4 av[2];
     const bool two = v + stride < nvec;
     LabelVec<LT>::load(p.labels, v, g[0]);
     av[0] = ldg_stream16((const int4*)p.a + v);
     if (two) { LabelVec<LT>::load(p.labels, v + stride, g[1]); av[1] = ldg_stream16((const int4*)p.a + v + stride); }
+    else {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      update(g[u][0], __int_as_float(av[u].x)); update(g[u][1], __int_as_float(av[u].y));
-      update(g[u][2], __int_as_float(av[u].z)); update(g[u][3], __int_as_float(av[u].w));
+      for (int k = 0; k < 4; ++k) g[1][k] = -1;
+      av[1] = make_int4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int b0 = 0; b0 < 8; b0 += MF_B) {
+      unsigned t[MF_B], cur[MF_B];
+#pragma unroll
+      for (int e = 0; e < MF_B; ++e) {
+        const int u = (b0 + e) >> 2, k = (b0 + e) & 3;
+        const long long gg = g[u][k];
+        const float x = __int_as_float(k == 0 ? av[u].x : (k == 1 ? av[u].y : (k == 2 ? av[u].z : av[u].w)));
+        const bool nan = x != x;
+        const int k32 = nan ? (ISMAX ? 0x7fffffff : (int)0x80000000) : key32_of(x);            // NaN wins
+        const unsigned uu = ISMAX ? ((unsigned)k32 ^ 0x80000000u) : ~((unsigned)k32 ^ 0x80000000u);  // larger uu = better
+        t[e] = uu >> 16;
+        const bool ok = (unsigned long long)gg < (unsigned long long)p.size;
+        if (!ok && (u == 0 || two)) bad = true;
+        cur[e] = (ok && !(nan && nanskip)) ? (gg < p.cov ? (unsigned)top[gg] : 0u) : 0xffffu;  // 0xffff rejects everything
+      }
+#pragma unroll
+      for (int e = 0; e < MF_B; ++e) {
+        if (t[e] < cur[e] || cur[e] == 0xffffu) continue;
+        const int u = (b0 + e) >> 2, k = (b0 + e) & 3;
+        const long long gg = g[u][k];
+        const float x = __int_as_float(k == 0 ? av[u].x : (k == 1 ? av[u].y : (k == 2 ? av[u].z : av[u].w)));
+        const long long k64 = x != x ? (ISMAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
+        if (TIE && t[e] == cur[e]) {
+          // skewed labels (the probe says so): a tie in the upper 16 bits looks at the exact value in the global table
+          // first (L2 read; a stale value only costs a redundant RED).  Keeps the ties of a HOT group -- thousands per
+          // CTA -- from queueing on one L2 address (Zipf, 10^5 groups: 277-325 -> 373 Gelem/s); on uniform labels the
+          // extra round trip per tie costs 15 %, so that variant runs without it.
+          const long long seen = __ldcg(p.t.t0i + gg);
+          if (ISMAX ? k64 <= seen : k64 >= seen) continue;
+        }
+        if (ISMAX) red_max_s64_hint(p.t.t0i + gg, k64, pol); else red_min_s64_hint(p.t.t0i + gg, k64, pol);
+        if (t[e] > cur[e] && gg < p.cov) top[gg] = (unsigned short)t[e];
+      }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {
@@ -395,15 +457,15 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_maxfilter(const FastParams 
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = ISMAX ? 17 : 18;
 }
-template <bool ISMAX, class LT>
+template <bool ISMAX, class LT, bool TIE>
 inline int launch_maxfilter(const FastParams& p, cudaStream_t st, int sms) {
-  auto kern = k_maxfilter<ISMAX, LT>;
+  auto kern = k_maxfilter<ISMAX, LT, TIE>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
     attr_done = true;
   }
-  const size_t smem = (size_t)((p.size + 1) / 2) * 4;
+  const size_t smem = (size_t)((p.cov + 1) / 2) * 4;
   AGC_COUNT_LAUNCH(1), kern<<<sms, FAST_THREADS, smem, st>>>(p);
   return 1;
 }

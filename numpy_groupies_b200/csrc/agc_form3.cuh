@@ -200,10 +200,12 @@ inline int try_form3_path(const agc_request_t* r, const Tables& t, cudaStream_t 
   else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
   else mode = FM_SUM;
   const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
-  const size_t cap = 108 * 1024;
+  // two CTAs per SM: up to 2 x 97 KB the L1 keeps 60 KB for the loads in flight (see AGC_SMEM1 in agc_dispatch.cuh); a single
+  // row block may go up to 110 KB (slower streaming, still far ahead of the general kernel)
+  const size_t cap = 97 * 1024, cap_max = 110 * 1024;
   int rb = 4;                                              // 8 rows of 128-bit loads would spill at 64 registers / thread
   while (rb > 1 && (size_t)rb * G * words * 4 > cap) rb >>= 1;
-  if ((size_t)rb * G * words * 4 > cap) return 0;
+  if ((size_t)rb * G * words * 4 > cap_max) return 0;
   while (rb > 1 && rows < rb) rb >>= 1;
 
   Form3Params p;

@@ -14,8 +14,8 @@
 namespace agc {
 
 constexpr int SMALL_THREADS = 512;
-constexpr size_t SMALL_SMEM = 48 * 1024;        // 4 CTAs/SM, replicated tables
-constexpr size_t SMALL_SMEM_BIG = 200 * 1024;   // up to ~17 K groups: one unreplicated table per SM
+constexpr size_t SMALL_SMEM = 47 * 1024;        // 4 CTAs/SM, replicated tables (4 x (47 + 1) KB <= 196 KB per SM)
+constexpr size_t SMALL_SMEM_BIG = 194 * 1024;   // up to ~16.5 K groups: one unreplicated table per SM (<= 196 KB per SM keeps 60 KB of L1)
 
 __device__ __forceinline__ void smem_mul_f64(double* addr, double v) {
   unsigned long long* a = (unsigned long long*)addr;
