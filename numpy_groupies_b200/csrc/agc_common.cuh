@@ -212,4 +212,9 @@ __device__ __forceinline__ void red_min_s64_hint(long long* addr, long long v, u
   asm volatile("red.global.min.L2::cache_hint.s64 [%0], %1, %2;" :: "l"(addr), "l"(v), "l"(pol) : "memory");
 }
 
+// shared-memory RED (no return value) on a 32-bit shared-window address
+__device__ __forceinline__ void reds_add_u32(unsigned saddr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+
 }  // namespace agc

@@ -255,13 +255,14 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_len16: counts with 16-bit counters, two per shared-memory word -- up to 113 K groups per SM.
+// k_len16: counts with 16-bit counters, two per shared-memory word -- ~100 K groups in 195 KB.
 // `len`, and the count pass of the split mean / var on tables the one-word sum kernel also covers.
-// A counter uses 15 bits: the thread whose ATOMS.ADD returns a half equal to 0x7FFF (it made it 0x8000) takes
-// 0x8000 out of that half again and forwards 32768 to the global count.  Safety: the CTA runs a __syncthreads()
-// per tile of 16384 elements, so at most 16384 adds can land on a half between a detection and
-// its fix-up -- the half stays below 0x8000 + 1 + 16384 < 0xFFFF and never carries into its neighbour, and no second
-// thread can see 0x7FFF before the fix (that would need a wrap).  (The tile is 4 vectors per thread = 16384 adds.)
+// An element reads its counter word (plain LDS), then adds 1 to its half with a shared-memory RED (no return value,
+// no barrier anywhere).  A thread that READS a half >= 0x8000 takes 0x8000 out of it with a CAS and forwards 32768 to
+// the global count before it adds.  Why a half can never carry into its neighbour: an add is "blind" only if its LDS
+// came before the half crossed 0x8000; a thread issues the LDS of a batch of 8 elements before their adds, so at most
+// 1024 x 8 blind adds can follow a crossing -- the half stays below 0x8000 + 8192 + 8192 < 0x10000 until the next
+// reader repairs it, and the final merge reads all 16 bits.
 // ---------------------------------------------------------------------------------------------
 template <class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
@@ -270,69 +271,62 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
   const int W = (p.cov + 1) >> 1;                              // groups [0, cov) have a counter, the rest go straight to the global table
   for (int i = threadIdx.x; i < W; i += blockDim.x) sw[i] = 0u;
   __syncthreads();
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sw);
   const long long nvec = p.n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool nanskip = p.flags & AGC_F_NANSKIP;
   const unsigned long long pol = l2_evict_last_policy();
   bool bad = false;
-  auto update = [&](long long g, float x) {
+  // take 0x8000 out of the half `sh` of word `wi` (if it still is >= 0x8000) and forward it to the global count
+  auto repair = [&](int wi, int sh, long long g) {
+    unsigned o = *(volatile unsigned*)(sw + wi);
+    while (((o >> sh) & 0xffffu) >= 0x8000u) {
+      const unsigned seen = atomicCAS(sw + wi, o, o - (0x8000u << sh));
+      if (seen == o) { red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 0x8000ull, pol); break; }
+      o = seen;
+    }
+  };
+  auto update = [&](long long g, float x) {                  // one element at a time (ragged tail)
     if ((unsigned long long)g >= (unsigned long long)p.size) { bad = true; return; }
     if (LOAD_A && nanskip && x != x) return;
     if (g >= p.cov) { red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol); return; }
-    const int sh = ((int)g & 1) << 4;
-    const unsigned old = atomicAdd(sw + ((int)g >> 1), 1u << sh);
-    if (((old >> sh) & 0xffffu) == 0x7fffu) {
-      atomicSub(sw + ((int)g >> 1), 0x8000u << sh);
-      red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 0x8000ull, pol);
-    }
+    const int sh = ((int)g & 1) << 4, wi = (int)g >> 1;
+    if (((*(volatile unsigned*)(sw + wi) >> sh) & 0xffffu) >= 0x8000u) repair(wi, sh, g);
+    reds_add_u32(sbase + wi * 4, 1u << sh);
   };
-  // block-uniform trip count: every thread reaches the barrier of every tile.  A tile is LEN16_U vectors per thread =
-  // 8192 elements (< 0x7FFF adds between a detection and its fix-up).  Two register stages: the loads of tile t+1 are
-  // issued before tile t is counted, so the barrier does not expose the load latency.
-  constexpr int LEN16_U = 2;
-  struct Stage { long long g[LEN16_U][4]; float x[LEN16_U][4]; bool in[LEN16_U]; };
-  auto load_tile = [&](Stage& s, long long vb) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += 2 * stride) {
+    long long g[2][4]; float x[2][4];
+    const bool two = v + stride < nvec;
 #pragma unroll
-    for (int u = 0; u < LEN16_U; ++u) {
-      const long long v = vb + u * stride + threadIdx.x;
-      s.in[u] = v < nvec;
+    for (int u = 0; u < 2; ++u) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { s.g[u][k] = 0; s.x[u][k] = 0.f; }
-      if (s.in[u]) {
-        LabelVec<LT>::load(p.labels, v, s.g[u]);
+      for (int k = 0; k < 4; ++k) { g[u][k] = -1; x[u][k] = 0.f; }
+      if (u == 0 || two) {
+        LabelVec<LT>::load(p.labels, v + u * stride, g[u]);
         if (LOAD_A) {
-          int4 av = ldg_stream16((const int4*)p.a + v);
-          s.x[u][0] = __int_as_float(av.x); s.x[u][1] = __int_as_float(av.y); s.x[u][2] = __int_as_float(av.z); s.x[u][3] = __int_as_float(av.w);
+          int4 av = ldg_stream16((const int4*)p.a + v + u * stride);
+          x[u][0] = __int_as_float(av.x); x[u][1] = __int_as_float(av.y); x[u][2] = __int_as_float(av.z); x[u][3] = __int_as_float(av.w);
         }
       }
     }
-  };
-  auto count_tile = [&](const Stage& s) {
+    unsigned cur[8];                                          // counter words of the batch, all read before the first add
 #pragma unroll
-    for (int u = 0; u < LEN16_U; ++u) {
-      if (!s.in[u]) continue;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) update(s.g[u][k], s.x[u][k]);
+    for (int e = 0; e < 8; ++e) {
+      const long long gg = g[e >> 2][e & 3];
+      const bool ok = (unsigned long long)gg < (unsigned long long)p.size;
+      if (!ok && (e < 4 || two)) bad = true;
+      const bool take = ok && !(LOAD_A && nanskip && x[e >> 2][e & 3] != x[e >> 2][e & 3]);
+      // 0xffffffff: skip; covered groups read their word; uncovered groups are marked with 0xfffffffe
+      cur[e] = !take ? 0xffffffffu : (gg < p.cov ? *(volatile unsigned*)(sw + ((int)gg >> 1)) : 0xfffffffeu);
     }
-    __syncthreads();
-  };
-  {
-    const long long tile = stride * LEN16_U;
-    long long vb = (long long)blockIdx.x * blockDim.x;
-    if (vb < nvec) {
-      Stage sa, sb;
-      load_tile(sa, vb);
-      for (;;) {
-        const bool more1 = vb + tile < nvec;
-        if (more1) load_tile(sb, vb + tile);
-        count_tile(sa);
-        if (!more1) break;
-        const bool more2 = vb + 2 * tile < nvec;
-        if (more2) load_tile(sa, vb + 2 * tile);
-        count_tile(sb);
-        if (!more2) break;
-        vb += 2 * tile;
-      }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (cur[e] == 0xffffffffu) continue;
+      const long long gg = g[e >> 2][e & 3];
+      if (gg >= p.cov) { red_add_u64_hint((unsigned long long*)(p.t.t1 + gg), 1ull, pol); continue; }
+      const int sh = ((int)gg & 1) << 4, wi = (int)gg >> 1;
+      if (((cur[e] >> sh) & 0xffffu) >= 0x8000u) repair(wi, sh, gg);
+      reds_add_u32(sbase + wi * 4, 1u << sh);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {

@@ -448,7 +448,7 @@ def test_len16_counter_overflow_is_forwarded_exactly():
     (same word) must not disturb each other and nothing may be lost."""
     from numpy_groupies_b200 import aggregate_cuda as ac
     rng = np.random.default_rng(97)
-    n, groups = (1 << 23) + 3, 100000
+    n, groups = (1 << 25) + 3, 100000          # ~100 K adds per hot group and CTA: each wraps the 15-bit range three times
     gidx = rng.integers(0, groups, n)
     hot = rng.random(n)
     gidx[hot < 0.45] = 4242            # even group: low half of its word
@@ -466,8 +466,38 @@ def test_len16_counter_overflow_is_forwarded_exactly():
         with np.errstate(all="ignore"):
             ref = oracle.aggregate(gidx, a, func="nanmean", size=groups)
         np.testing.assert_allclose(m, ref, rtol=1e-5, equal_nan=True)
+        # worst case for the read-check-repair protocol: every thread of every CTA hammers the same half
+        one = np.full(1 << 24, 77777, dtype=np.int64)
+        one[::4097] = 77776
+        got = aggregate(one, 1.0, func="len", size=groups)
+        assert ac.last_regime() == 16, ac.last_regime()
+        np.testing.assert_array_equal(got, np.bincount(one, minlength=groups))
+        # groups beyond the counter table (size > ~99 800) go straight to the global counts
+        big = 130000
+        gb = rng.integers(0, big, 1 << 22)
+        got = aggregate(gb, 1.0, func="len", size=big)
+        assert ac.last_regime() == 16, ac.last_regime()
+        np.testing.assert_array_equal(got, np.bincount(gb, minlength=big))
     finally:
         ac.tuning(large=1)
+
+
+@pytest.mark.parametrize("groups", [99776, 99778, 150000, 400000])
+@pytest.mark.parametrize("func", ["max", "nanmin"])
+def test_max_min_filter_kernel_partial_table(func, groups):
+    """Sizes around and beyond what the 16-bit filter table covers (99 776 groups in 195 KB): the groups past the table
+    always pass the filter and go to the global table directly."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(groups + len(func))
+    n = (1 << 21) + 1
+    gidx = rng.integers(0, groups, n)
+    a = rng.standard_normal(n).astype(np.float32)
+    a[rng.random(n) < 0.02] = np.nan
+    got = aggregate(gidx, a, func=func, size=groups, fill_value=7)
+    assert ac.last_regime() == (17 if func == "max" else 18), ac.last_regime()
+    with np.errstate(all="ignore"):
+        ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=7)
+    np.testing.assert_array_equal(got, ref)
 
 
 @pytest.mark.parametrize("dist", ["uniform", "zipf", "sorted"])
