@@ -160,7 +160,10 @@ int64_t     agc_launch_count(void);
  *   key 0  strategy for tables larger than one SM's shared memory: 0 hot-key cache, 1 on-device label probe
  *          decides (default), 3 always partial table + global RED, 4 always the run kernel (segmented warp reduce)
  *   key 1  CTAs per SM of the hot-key-cache kernel (1 | 2)
- *   key 2  large tables: one-word sums with carry forwarding and split mean (1, default) or fused tables (0) */
+ *   key 2  large tables: one-word sums with carry forwarding and split mean (1, default) or fused tables (0)
+ *   key 3  bytes of shared memory one CTA per SM may use for its table (default 199552: <= 196 KB per SM keeps 60 KB
+ *          of L1 for the global loads in flight; the 228 KB carve-out costs a third of the streaming bandwidth)
+ *   key 4  the same per CTA for kernels that run two CTAs per SM (default 99200) */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus
