@@ -176,13 +176,27 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
     AGC_COUNT_LAUNCH(1);
     p.choose = r->status + 4; p.want = 0;
-    p.cov = (int)(r->size < cov16 ? r->size : cov16);        // groups beyond the filter table always pass (one RED each)
+    // labels the probe calls uniform: groups past the filter table always pass (one RED each; no group holds more than
+    // ~0.1 % of the elements, so none of them can pile more than ~1.5 ms of REDs on one address)
+    p.cov = (int)(r->size < cov16 ? r->size : cov16);
     if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long, false>(p, st, sms) : launch_maxfilter<true, int, false>(p, st, sms);
     else rc = i64 ? launch_maxfilter<false, long long, false>(p, st, sms) : launch_maxfilter<false, int, false>(p, st, sms);
     if (rc < 0) return rc;
-    p.want = 1;                                              // skewed labels: the same kernel with the exact test on ties
-    if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long, true>(p, st, sms) : launch_maxfilter<true, int, true>(p, st, sms);
-    else rc = i64 ? launch_maxfilter<false, long long, true>(p, st, sms) : launch_maxfilter<false, int, true>(p, st, sms);
+    // skewed labels: a hot group must never be one of the uncovered ones (ONE such group with 1.5 % of the elements costs
+    // 18 ms of serialised REDs).  Up to 113 K groups the whole table fits (in the 228 KB carve-out: slower streaming, no
+    // hazard) and ties get the exact test; beyond that the hot-key cache takes over.
+    p.want = 1;
+    if ((size_t)((r->size + 1) / 2) * 4 <= cap_max) {
+      p.cov = (int)r->size;
+      if (mode == FM_MAX) rc = i64 ? launch_maxfilter<true, long long, true>(p, st, sms) : launch_maxfilter<true, int, true>(p, st, sms);
+      else rc = i64 ? launch_maxfilter<false, long long, true>(p, st, sms) : launch_maxfilter<false, int, true>(p, st, sms);
+    } else {
+      const int ctas = env_cache_ctas;
+      const size_t budget = ctas == 2 ? 110 * 1024 : cap_max;
+      p.cov = (int)r->size;
+      p.nslots = (int)(budget / ((1 + words) * 4)) & ~1;
+      chunked(ctas, (size_t)p.nslots * (1 + words) * 4, true);
+    }
     if (rc < 0) return rc;
     p.want = 2; p.cov = (int)r->size;
     AGC_FAST_ALL(launch_runs, p, st, sms)

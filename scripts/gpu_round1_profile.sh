@@ -15,7 +15,7 @@ $B3 cumsum 28 1000000 sorted > gpurun_out/plain_f.log 2>&1 && ncu --set full --c
 $B3 cumsum 28 1000000 unsorted > gpurun_out/plain_g.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_radix_scatter -s 3 -c 1 -f -o gpurun_out/prof_radix_scatter $B3 cumsum 28 1000000 unsorted > gpurun_out/ncu_g.log 2>&1
 $B3 sum 28 100 unsorted float64 > gpurun_out/plain_i.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_accumulate_small -s 1 -c 1 -f -o gpurun_out/prof_small_f64_G100 $B3 sum 28 100 unsorted float64 > gpurun_out/ncu_i.log 2>&1
 B5="python bench.py --steps 2 --warmup 3 --no-sweep --no-e2e --cpu-log2n 16 --func max"
-$B5 > gpurun_out/plain_j.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_maxfilter -s 3 -c 1 -f -o gpurun_out/prof_maxfilter_G1e5 $B5 > gpurun_out/ncu_j.log 2>&1
+$B5 > gpurun_out/plain_j.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_maxfilter -s 6 -c 1 -f -o gpurun_out/prof_maxfilter_G1e5 $B5 > gpurun_out/ncu_j.log 2>&1
 B6="python bench.py --steps 2 --warmup 3 --no-sweep --no-e2e --cpu-log2n 16 --func mean"
 $B6 > gpurun_out/plain_k.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_len16 -s 3 -c 1 -f -o gpurun_out/prof_len16_G1e5 $B6 > gpurun_out/ncu_k.log 2>&1
 for f in gpurun_out/prof_*.ncu-rep; do
