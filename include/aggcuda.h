@@ -163,7 +163,9 @@ int64_t     agc_launch_count(void);
  *   key 2  large tables: one-word sums with carry forwarding and split mean (1, default) or fused tables (0)
  *   key 3  bytes of shared memory one CTA per SM may use for its table (default 199552: <= 196 KB per SM keeps 60 KB
  *          of L1 for the global loads in flight; the 228 KB carve-out costs a third of the streaming bandwidth)
- *   key 4  the same per CTA for kernels that run two CTAs per SM (default 99200) */
+ *   key 4  the same per CTA for kernels that run two CTAs per SM (default 99200)
+ *   key 5  a partial table keeps the key-3 size while at most this percentage of the groups stays uncovered; beyond
+ *          that it grows to the full 226 KB (default 10) */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus

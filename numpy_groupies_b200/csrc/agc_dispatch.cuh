@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
 //                         in flight -- a streaming kernel then reaches 350-370 instead of 500-590 Gelem/s
 //                         (measured cliff between 196 000 and 200 000 B of table, profiles/r01d_smem_carveout_cliff.jsonl)
 //   key 4  AGC_SMEM2      the same for kernels that run two CTAs per SM (default 99200)
-enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_COUNT = 5 };
-static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1};
+//   key 5  AGC_UNCOV_PCT  a partial table keeps the 195 KB size while at most this percentage of the groups stays uncovered,
+//                         beyond that it grows to 226 KB (default 10; measured crossover 9-17 %, scripts/uncov_sweep.py)
+enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_UNCOV = 5, TUNE_COUNT = 6 };
+static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1, -1};
 inline void tuning_defaults() {
   if (g_tune[0] >= 0) return;
   const char* e;
@@ -80,6 +82,7 @@ inline void tuning_defaults() {
   e = getenv("AGC_SUM1");       g_tune[TUNE_SUM1] = (e && atoi(e) == 0) ? 0 : 1;
   e = getenv("AGC_SMEM1");      g_tune[TUNE_SMEM1] = e ? atoi(e) : 199552;
   e = getenv("AGC_SMEM2");      g_tune[TUNE_SMEM2] = e ? atoi(e) : 99200;
+  e = getenv("AGC_UNCOV_PCT");  g_tune[TUNE_UNCOV] = e ? atoi(e) : 10;
 }
 inline size_t smem_cap1() { int v = g_tune[TUNE_SMEM1]; return (size_t)(v < 16384 ? 16384 : (v > 227 * 1024 - 1024 ? 227 * 1024 - 1024 : v)); }
 inline size_t smem_cap2() { int v = g_tune[TUNE_SMEM2]; return (size_t)(v < 8192 ? 8192 : (v > 110 * 1024 ? 110 * 1024 : v)); }
@@ -163,7 +166,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   auto pick_cov = [&](size_t bpg_num, size_t bpg_den) -> long long {      // bytes per group = bpg_num / bpg_den
     const long long fast = (long long)(cap1 * bpg_den / bpg_num), big = (long long)(cap_max * bpg_den / bpg_num);
     if (r->size <= fast) return r->size;
-    if (cap1 >= cap_max || (double)(r->size - fast) <= 0.15 * (double)r->size) return fast & ~1ll;
+    if (cap1 >= cap_max || (double)(r->size - fast) <= 0.01 * g_tune[TUNE_UNCOV] * (double)r->size) return fast & ~1ll;
     return (r->size < big ? r->size : big) & ~1ll;
   };
   const long long cov16 = pick_cov(2, 1);                    // groups a table of 16-bit entries covers
