@@ -87,6 +87,46 @@ inline void tuning_defaults() {
 inline size_t smem_cap1() { int v = g_tune[TUNE_SMEM1]; return (size_t)(v < 16384 ? 16384 : (v > 227 * 1024 - 1024 ? 227 * 1024 - 1024 : v)); }
 inline size_t smem_cap2() { int v = g_tune[TUNE_SMEM2]; return (size_t)(v < 8192 ? 8192 : (v > 110 * 1024 ? 110 * 1024 : v)); }
 
+// second pass of var / std (T0 holds the means, T2 takes sum (a - mean)^2): shared-memory tables for f32 data and f32
+// results while one SM holds a sum word per group.  Returns 1 if it ran, 0 to fall back to the general kernel.
+inline int try_fast_pass2(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
+  if (r->op != AGC_OP_VAR || r->index.form != AGC_FORM_FLAT) return 0;
+  if (r->index.dtype != AGC_DT_I64 && r->index.dtype != AGC_DT_I32) return 0;
+  if (r->a == nullptr || r->a_dtype != AGC_DT_F32 || r->out_dtype != AGC_DT_F32) return 0;
+  if (r->n < (1 << 16) || r->size >= (1ll << 31)) return 0;
+  if (((uintptr_t)r->index.labels & 15) || ((uintptr_t)r->a & 15)) return 0;
+  tuning_defaults();
+  if (g_tune[TUNE_SUM1] == 0) return 0;
+  const size_t cap2 = smem_cap2(), cap1 = smem_cap1();
+  const bool two_word = (size_t)r->size * 8 <= cap1;          // exact 16-binade window
+  if (!two_word && (size_t)r->size * 4 > cap1) return 0;      // a partial table would need the label probe: general kernel
+  FastParams p;
+  p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
+  p.t.t0f = t.t2; p.means = t.t0f;
+  p.flags = r->flags & AGC_F_NANSKIP; p.square = 0; p.want_b1 = 0; p.want_cnt = 0;
+  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size;
+  const bool i64 = r->index.dtype == AGC_DT_I64;
+  const size_t table = (size_t)r->size * (two_word ? 8 : 4);
+  // up to 12.4 K groups the means ride along in shared memory (8 more bytes per group): an LDS instead of an L2 round
+  // trip per element
+  const size_t mbytes = (size_t)r->size * 8 + 8;
+  p.means_smem = table + mbytes <= cap1 ? 1 : 0;
+  const size_t extra = p.means_smem ? mbytes : 0;
+  const int ctas = table + extra <= cap2 ? 2 : 1;
+  if (ctas == 2) while (p.rshift < 5 && (table << (p.rshift + 1)) + extra <= cap2) ++p.rshift;
+  const size_t smem = (table << p.rshift) + extra;
+  const long long per_launch = (long long)sms * ctas * FAST_MAX_PER_CTA;
+  int rc = 1;
+  for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
+    p.n = r->n - off < per_launch ? r->n - off : per_launch;
+    p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
+    p.a = (const float*)r->a + off;
+    if (two_word) rc = i64 ? launch_fast<FM_SUM, long long, true>(p, ctas, smem, st, sms) : launch_fast<FM_SUM, int, true>(p, ctas, smem, st, sms);
+    else          rc = i64 ? launch_fast<FM_SUM1, long long, true>(p, ctas, smem, st, sms) : launch_fast<FM_SUM1, int, true>(p, ctas, smem, st, sms);
+  }
+  return rc < 0 ? rc : 1;
+}
+
 // returns 1 if it accumulated into the global tables (which it also initialises), 0 to fall back
 inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
   if (r->index.form == AGC_FORM_AXIS) return try_form3_path(r, t, st, sms);
@@ -122,7 +162,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
   p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
   p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
-  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size;
+  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size; p.means = nullptr; p.means_smem = 0;
   AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
   const bool i64 = r->index.dtype == AGC_DT_I64;
   int rc = 0;
@@ -149,6 +189,21 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     }
     p.n = r->n; p.labels = r->index.labels; p.a = (const float*)r->a;
   };
+
+  // mean / var (and sums that report touched groups) on 16.6 K - 24.9 K groups: one-word sums + u32 counts, 8 B per group,
+  // still fit one SM in one pass
+  if (!direct && mode == FM_SUMCNT && g_tune[TUNE_SUM1] != 0 && (size_t)r->size * 8 <= cap1) {
+    const long long per_launch = (long long)sms * FAST_MAX_PER_CTA;
+    const size_t smem = (size_t)r->size * 8;
+    for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
+      p.n = r->n - off < per_launch ? r->n - off : per_launch;
+      p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
+      p.a = (const float*)r->a + off;
+      if (i64) rc = launch_fast<FM_SUMCNT1, long long, true>(p, 1, smem, st, sms);
+      else     rc = launch_fast<FM_SUMCNT1, int, true>(p, 1, smem, st, sms);
+    }
+    return rc;
+  }
 
   if (direct) {
     const int ctas = table <= cap2 ? 2 : 1;

@@ -23,7 +23,8 @@
 
 namespace agc {
 
-enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4, FM_SUM1 = 5 };
+enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4, FM_SUM1 = 5, FM_SUMCNT1 = 6 };
+// FM_SUMCNT1: FM_SUM1's one-word sum + a u32 count (8 B per group instead of FM_SUMCNT's 12): mean / var on tables of 16.6 K - 24.9 K groups
 // FM_SUM1: ONE 32-bit word per group (k_fast only).  The word starts at 2^31 and takes q = x * 2^(FX1_F - E) with a
 // native ATOMS.ADD that returns the old value; a carry / borrow out of the word (the add crossed 0 or 2^32) is
 // forwarded at once as one exact f64 RED of +-2^32 units to the global table, so no bit is ever lost and there is
@@ -56,6 +57,8 @@ struct FastParams {
   int cov;              // k_fast: groups [0, cov) live in shared memory, the rest go straight to the global tables
   const int* choose;    // device word written by k_skew_probe; run iff *choose == want (NULL: always)
   int want;
+  const double* means;  // second pass of var / std: accumulate (float)((a - means[g])^2) instead of a (NULL: off)
+  int means_smem;       // ... with a copy of the means in shared memory behind the table (size * 8 more bytes)
 };
 
 __device__ __forceinline__ void fx_add(unsigned* lo, unsigned* hi, long long q) {
@@ -91,17 +94,26 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   if (p.choose && *p.choose != p.want) return;
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
-  constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
-  constexpr bool IS_SUM = MODE == FM_SUM || MODE == FM_SUMCNT || MODE == FM_SUM1;
-  constexpr int FXF = MODE == FM_SUM1 ? FX1_F : FX_F, FXW = MODE == FM_SUM1 ? FX1_WINDOW : FX_WINDOW;
+  constexpr bool ONEWORD = MODE == FM_SUM1 || MODE == FM_SUMCNT1;
+  constexpr bool HAS_CNT = MODE == FM_SUMCNT || MODE == FM_SUMCNT1;
+  constexpr int WORDS = (MODE == FM_SUM || MODE == FM_SUMCNT1) ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
+  constexpr bool IS_SUM = MODE == FM_SUM || MODE == FM_SUMCNT || ONEWORD;
+  constexpr int FXF = ONEWORD ? FX1_F : FX_F, FXW = ONEWORD ? FX1_WINDOW : FX_WINDOW;
   const int rs = p.rshift;
   const int G = p.cov << rs;                       // table entries incl. replicas: entry = (g << rs) | (lane & (R-1))
   const int rsel = (threadIdx.x & 31) & ((1 << rs) - 1);
   unsigned* w0 = sw;            // sum.lo | key | count(FM_LEN)
-  unsigned* w1 = sw + G;        // sum.hi
+  unsigned* w1 = sw + G;        // sum.hi | count (FM_SUMCNT1)
   unsigned* w2 = sw + 2 * G;    // count (FM_SUMCNT)
-  const unsigned init0 = (MODE == FM_MAX || MODE == FM_SUM1) ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
+  unsigned* wc = MODE == FM_SUMCNT1 ? w1 : w2;
+  const unsigned init0 = (MODE == FM_MAX || ONEWORD) ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
   for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;   // G counts replicas
+  const double* mtab = p.means;                    // where update() finds the group means (second pass of var / std)
+  if (IS_SUM && p.means && p.means_smem) {
+    double* sm = (double*)(sw + ((WORDS * G + 1) & ~1));
+    for (int i = threadIdx.x; i < (int)p.size; i += blockDim.x) sm[i] = p.means[i];
+    mtab = sm;
+  }
   if (threadIdx.x == 0) s_maxbits = 0u;
   __syncthreads();
 
@@ -118,10 +130,17 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     if (v < nvec) {
       int4 av = ldg_stream16((const int4*)p.a + v);
       unsigned b[4] = {(unsigned)av.x & 0x7fffffffu, (unsigned)av.y & 0x7fffffffu, (unsigned)av.z & 0x7fffffffu, (unsigned)av.w & 0x7fffffffu};
+      long long gs[4] = {0, 0, 0, 0};
+      if (p.means) LabelVec<LT>::load(p.labels, v, gs);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         unsigned bb = b[k];
         if (p.square) { float f = __uint_as_float(bb); bb = __float_as_uint(f * f); }
+        if (p.means) {
+          const float xk = __int_as_float(k == 0 ? av.x : (k == 1 ? av.y : (k == 2 ? av.z : av.w)));
+          const double d = (gs[k] >= 0 && gs[k] < p.size) ? (double)xk - p.means[gs[k]] : 0.0;
+          bb = __float_as_uint((float)(d * d));
+        }
         if (bb < 0x7f800000u && bb > m) m = bb;
       }
     }
@@ -131,7 +150,11 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     int eb = (int)(s_maxbits >> 23);            // biased exponent of the largest finite |value| seen
     if (eb == 0) eb = 127;                      // tile was all zero / non-finite: assume O(1) data
     eb += 1;                                    // values with biased exponent < eb convert
-    int lo_e = eb - FXW; if (lo_e < 1) lo_e = 1;
+    // squared deviations (second pass of var / std, f32 results) spread over many binades: the one-word format then also
+    // takes values down to 2^-12 of the reference, rounded to its grid (relative error of one term <= 2^-18, far below the
+    // 2^-24 already spent on rounding the squared deviation to f32 times the number of terms it would take to matter)
+    const int window = (ONEWORD && p.means) ? 12 : FXW;
+    int lo_e = eb - window; if (lo_e < 1) lo_e = 1;
     lo_bits = (unsigned)lo_e << 23;
     span_bits = (unsigned)(eb - lo_e) << 23;
     // q = v * 2^(FXF - (eb-127)) ; exact for in-window values
@@ -153,11 +176,12 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     } else {
       if (p.square) x = x * x;
       if ((__float_as_uint(x) & 0x7fffffffu) != 0u) { if (PARTIAL) red_add_f64_hint(p.t.t0f + g, (double)x, pol); else atomicAdd(p.t.t0f + g, (double)x); }
-      if (MODE == FM_SUMCNT) { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
+      if (HAS_CNT) { if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); if (p.want_b1) p.t.b1[g] = 1; }
     }
   };
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
+    if (IS_SUM && p.means) { const double d = (double)x - mtab[g]; x = (float)(d * d); }
     if (PARTIAL && g >= p.cov) { direct_global(g, x); return; }
     const int gi = ((int)g << rs) | rsel;
     if (MODE == FM_LEN) {
@@ -173,7 +197,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       if (p.square) x = x * x;
       unsigned ab = __float_as_uint(x) & 0x7fffffffu;
       if (ab - lo_bits < span_bits) {
-        if (MODE == FM_SUM1) {
+        if (ONEWORD) {
           const int q = __double2int_rn((double)x * scale);                 // |q| < 2^29, exact
           const unsigned old = atomicAdd(w0 + gi, (unsigned)q);
           const int net = (q >> 31) + (int)(old + (unsigned)q < old);         // carry (+1) / borrow (-1) out of the word
@@ -185,7 +209,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       } else if (ab != 0u) {
         atomicAdd(p.t.t0f + g, (double)x);          // out of window (huge / tiny / inf / NaN): exact f64 RED
       }
-      if (MODE == FM_SUMCNT) atomicAdd(w2 + gi, 1u);
+      if (HAS_CNT) atomicAdd(wc + gi, 1u);
     }
   };
 
@@ -216,7 +240,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     update(LabelVec<LT>::one(p.labels, i), LOAD_A ? p.a[i] : 0.f);
   }
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = 10 + MODE;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = MODE == FM_SUMCNT1 ? 19 : 10 + MODE;
   __syncthreads();
 
   // ---- merge the CTA's table into the global accumulator tables -----------------------------------
@@ -241,12 +265,12 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     } else {
       long long q = 0; unsigned long long c = 0;
       for (int r = 0; r < R; ++r) {
-        if (MODE == FM_SUM1) q += (long long)w0[e0 + r] - 0x80000000ll;              // residual around the 2^31 start value
+        if (ONEWORD) q += (long long)w0[e0 + r] - 0x80000000ll;                      // residual around the 2^31 start value
         else q += (long long)(((unsigned long long)w1[e0 + r] << 32) | w0[e0 + r]);  // <= 32 * 2^62 / 32: no overflow (FX_F headroom)
-        if (MODE == FM_SUMCNT) c += w2[e0 + r];
+        if (HAS_CNT) c += wc[e0 + r];
       }
       if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
-      if (MODE == FM_SUMCNT && c) {
+      if (HAS_CNT && c) {
         if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + gi), c);
         if (p.want_b1) p.t.b1[gi] = 1;
       }

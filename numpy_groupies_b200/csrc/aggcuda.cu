@@ -205,7 +205,12 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
         }
       }
       p.pass = 2;
-      launch_accumulate_cls(p, st);
+      int frc2 = 0;
+      if (r->op == AGC_OP_VAR && !(r->flags & AGC_F_NO_FAST) && r->n > 0 && r->size > 0) {
+        frc2 = agc::try_fast_pass2(r, t, st, sm_count());
+        if (frc2 < 0) return fail(frc2, "fast second pass launch failed");
+      }
+      if (frc2 == 0) launch_accumulate_cls(p, st);
       AGC_CUDA_OK("second pass");
     }
   }
