@@ -108,11 +108,17 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   unsigned* wc = MODE == FM_SUMCNT1 ? w1 : w2;
   const unsigned init0 = (MODE == FM_MAX || ONEWORD) ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
   for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;   // G counts replicas
-  const double* mtab = p.means;                    // where update() finds the group means (second pass of var / std)
+  // second pass of var / std with the means in shared memory: each mean as a (hi, lo) pair of floats (exact to 2^-48), so
+  // that the deviation is two f32 subtractions instead of f64 arithmetic (relative error ~1e-7 per term, unbiased)
+  const float2* mpair = nullptr;
   if (IS_SUM && p.means && p.means_smem) {
-    double* sm = (double*)(sw + ((WORDS * G + 1) & ~1));
-    for (int i = threadIdx.x; i < (int)p.size; i += blockDim.x) sm[i] = p.means[i];
-    mtab = sm;
+    float2* sm = (float2*)(sw + ((WORDS * G + 1) & ~1));
+    for (int i = threadIdx.x; i < (int)p.size; i += blockDim.x) {
+      const double m = p.means[i];
+      float2 hl; hl.x = (float)m; hl.y = (float)(m - (double)hl.x);
+      sm[i] = hl;
+    }
+    mpair = sm;
   }
   if (threadIdx.x == 0) s_maxbits = 0u;
   __syncthreads();
@@ -181,7 +187,10 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   };
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
-    if (IS_SUM && p.means) { const double d = (double)x - mtab[g]; x = (float)(d * d); }
+    if (IS_SUM && p.means) {
+      if (mpair) { const float2 hl = mpair[g]; const float d = (x - hl.x) - hl.y; x = d * d; }
+      else { const double d = (double)x - __ldg(p.means + g); x = (float)(d * d); }
+    }
     if (PARTIAL && g >= p.cov) { direct_global(g, x); return; }
     const int gi = ((int)g << rs) | rsel;
     if (MODE == FM_LEN) {
