@@ -12,7 +12,7 @@ if order == "sorted":
     lab = torch.sort(lab).values
 a = torch.randint(-2**31, 2**31, (n,), generator=gen, device="cuda") if dt == "int64" else torch.rand(n, generator=gen, device="cuda", dtype=getattr(torch, dt))
 torch.cuda.synchronize()
-for _ in range(2):
+for _ in range(int(os.environ.get("N_CALLS", "2"))):
     out = aggregate(lab, a, func=func, size=G, check=False)
 torch.cuda.synchronize()
 print("ok", out.shape)
