@@ -112,9 +112,11 @@ inline int try_fast_pass2(const agc_request_t* r, const Tables& t, cudaStream_t 
   const size_t mbytes = (size_t)r->size * 8 + 8;
   p.means_smem = table + mbytes <= cap1 ? 1 : 0;
   const size_t extra = p.means_smem ? mbytes : 0;
-  const int ctas = table + extra <= cap2 ? 2 : 1;
-  if (ctas == 2) while (p.rshift < 5 && (table << (p.rshift + 1)) + extra <= cap2) ++p.rshift;
-  const size_t smem = (table << p.rshift) + extra;
+  p.side = (two_word && 2 * table + extra <= cap1) ? 1 : 0;   // f64 side accumulator for what falls below the rounding window
+  const size_t tbytes = p.side ? 2 * table : table;
+  const int ctas = tbytes + extra <= cap2 ? 2 : 1;
+  if (ctas == 2) while (p.rshift < 5 && (tbytes << (p.rshift + 1)) + extra <= cap2) ++p.rshift;
+  const size_t smem = (tbytes << p.rshift) + extra;
   const long long per_launch = (long long)sms * ctas * FAST_MAX_PER_CTA;
   int rc = 1;
   for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
@@ -162,7 +164,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
   p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
   p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
-  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size; p.means = nullptr; p.means_smem = 0;
+  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size; p.means = nullptr; p.means_smem = 0; p.side = 0;
   AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
   const bool i64 = r->index.dtype == AGC_DT_I64;
   int rc = 0;
@@ -206,9 +208,13 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   }
 
   if (direct) {
-    const int ctas = table <= cap2 ? 2 : 1;
-    if (ctas == 2) while (p.rshift < 5 && (table << (p.rshift + 1)) <= cap2) ++p.rshift;   // replicate small tables
-    chunked(ctas, table << p.rshift, false);
+    // sums on small tables: 8 more bytes per entry for the f64 side accumulator (values outside the fixed-point window
+    // stay on chip instead of queueing as REDs on a few hot addresses)
+    size_t tbytes = table;
+    if ((mode == FM_SUM || mode == FM_SUMCNT) && (size_t)r->size * (words * 4 + 8) <= cap1) { p.side = 1; tbytes = (size_t)r->size * (words * 4 + 8); }
+    const int ctas = tbytes <= cap2 ? 2 : 1;
+    if (ctas == 2) while (p.rshift < 5 && (tbytes << (p.rshift + 1)) <= cap2) ++p.rshift;   // replicate small tables
+    chunked(ctas, (tbytes << p.rshift) + (p.side ? 8 : 0), false);        // + alignment pad in front of the side table
     return rc;
   }
 

@@ -59,7 +59,11 @@ struct FastParams {
   int want;
   const double* means;  // second pass of var / std: accumulate (float)((a - means[g])^2) instead of a (NULL: off)
   int means_smem;       // ... with a copy of the means in shared memory behind the table (size * 8 more bytes)
+  int side;             // k_fast sums: an f64 side accumulator per table entry (8 more bytes) takes what falls outside the fixed-point window
 };
+
+// one out-of-window value into the CTA's f64 side accumulator (shared memory, CAS loop) -- deliberately not inlined
+__device__ __noinline__ void smem_side_add(unsigned* side_words, int gi, double v) { atomicAdd((double*)side_words + gi, v); }
 
 __device__ __forceinline__ void fx_add(unsigned* lo, unsigned* hi, long long q) {
   unsigned ql = (unsigned)q; int qh = (int)(q >> 32);
@@ -110,9 +114,20 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;   // G counts replicas
   // second pass of var / std with the means in shared memory: each mean as a (hi, lo) pair of floats (exact to 2^-48), so
   // that the deviation is two f32 subtractions instead of f64 arithmetic (relative error ~1e-7 per term, unbiased)
+  // values outside the exact fixed-point window (huge / tiny / inf / NaN): on a small table their f64 REDs would queue
+  // on a few hot L2 addresses (log-uniform data over 20 binades, 100 groups: 21 ms instead of 0.5 ms at N = 2^28), so
+  // while it fits the CTA keeps an f64 side accumulator per table entry in shared memory (CAS-loop adds, used rarely
+  // for narrow data, and still >100 Gelem/s when half the data takes it)
+  double* side = nullptr;
+  int tail_words = (WORDS * G + 1) & ~1;                   // first free (8-byte aligned) word behind the table
+  if (IS_SUM && p.side) {
+    side = (double*)(sw + tail_words);
+    for (int i = threadIdx.x; i < G; i += blockDim.x) side[i] = 0.0;
+    tail_words += 2 * G;
+  }
   const float2* mpair = nullptr;
   if (IS_SUM && p.means && p.means_smem) {
-    float2* sm = (float2*)(sw + ((WORDS * G + 1) & ~1));
+    float2* sm = (float2*)(sw + tail_words);
     for (int i = threadIdx.x; i < (int)p.size; i += blockDim.x) {
       const double m = p.means[i];
       float2 hl; hl.x = (float)m; hl.y = (float)(m - (double)hl.x);
@@ -217,8 +232,11 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
           long long q = __double2ll_rn((double)x * scale);
           fx_add(w0 + gi, w1 + gi, q);
         }
-      } else if (ab != 0u) {
-        atomicAdd(p.t.t0f + g, (double)x);          // out of window (huge / tiny / inf / NaN): exact f64 RED
+      } else if (ab != 0u) {                        // out of window (huge / tiny / inf / NaN): f64, on chip if there is room
+        // (the side table's address is recomputed from the kernel parameters and the add is an out-of-line call: the hot
+        // loop of the 32-register variant has no room for another live pointer)
+        if (p.side) smem_side_add(sw + ((WORDS * (p.cov << p.rshift) + 1) & ~1), gi, (double)x);
+        else atomicAdd(p.t.t0f + g, (double)x);
       }
       if (HAS_CNT) atomicAdd(wc + gi, 1u);
     }
@@ -280,7 +298,10 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
         else q += (long long)(((unsigned long long)w1[e0 + r] << 32) | w0[e0 + r]);  // <= 32 * 2^62 / 32: no overflow (FX_F headroom)
         if (HAS_CNT) c += wc[e0 + r];
       }
-      if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
+      double tot = (double)q * inv_scale;
+      bool any = q != 0;
+      if (side) { for (int r = 0; r < R; ++r) { const double sv = side[e0 + r]; if (sv != 0.0) { tot += sv; any = true; } } }
+      if (any) atomicAdd(p.t.t0f + gi, tot);
       if (HAS_CNT && c) {
         if (p.want_cnt) atomicAdd((unsigned long long*)(p.t.t1 + gi), c);
         if (p.want_b1) p.t.b1[gi] = 1;

@@ -483,6 +483,27 @@ def test_len16_counter_overflow_is_forwarded_exactly():
         ac.tuning(large=1)
 
 
+@pytest.mark.parametrize("groups", [100, 5000, 12000])
+@pytest.mark.parametrize("func", ["sum", "mean", "nansum", "nanmean", "sumofsquares", "var"])
+def test_small_table_side_accumulator_for_wide_dynamic_range(func, groups):
+    """Data over 40 binades (and both signs): most values miss the CTA's fixed-point window and go through the f64 side
+    accumulator in shared memory instead of global REDs; inf / NaN travel the same way."""
+    rng = np.random.default_rng(groups + len(func))
+    n = (1 << 20) + 5
+    gidx = rng.integers(0, groups, n)
+    a = (np.exp2(rng.uniform(-20, 20, n)) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    if "nan" in func:
+        a[rng.random(n) < 0.05] = np.nan
+    if func in ("sum", "nansum"):
+        a[gidx == 7] = 1.5
+        a[np.flatnonzero(gidx == 7)[:1]] = np.inf            # one group with an infinity
+    got = aggregate(gidx, a, func=func, size=groups)
+    with np.errstate(all="ignore"):
+        ref = oracle.aggregate(gidx, a, func=func, size=groups)
+    assert got.dtype == ref.dtype
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5 * float(np.nanmax(np.abs(ref[np.isfinite(ref)]))), equal_nan=True)
+
+
 @pytest.mark.parametrize("dist", ["uniform", "zipf"])
 @pytest.mark.parametrize("func", ["mean", "nanmean", "var", "nanstd", "sum", "nansum"])
 def test_one_word_sum_and_count_table(func, dist):
