@@ -119,7 +119,7 @@ typedef struct agc_request {
   int32_t* status;                 /* device int32[8]; [0] bad label, [1] fast-path precision guard,    */
                                    /* [2] labels-not-sorted (ASSUME_SORTED violated), [3] regime used,  */
                                    /* [4..6] label probe: skewed?, largest bucket, equal neighbours;    */
-                                   /* [7] library scratch (work-item counter)                           */
+                                   /* [7] library scratch (Form 3 work counter / probe: values span > window) */
 } agc_request_t;
 
 /* one partial table inside the workspace after AGC_F_ACC_ONLY (for the multi-GPU merge) */

@@ -27,20 +27,37 @@ constexpr int PROBE_SAMPLES = 32768;                // at n >= 2^23; fewer for s
 // RED: a 0.5 % group doubles the partial-table kernel's time, 1.5 % makes it 5x) and the hot-key cache wins.
 constexpr int PROBE_SKEW_COUNT = 40;
 template <class LT>
-__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int samples, int thresh) {
+__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int samples, int thresh, const float* a = nullptr) {
   __shared__ unsigned cnt[4096];
-  __shared__ unsigned s_max, s_adj;
+  __shared__ unsigned s_max, s_adj, s_emax, s_low;
   for (int i = threadIdx.x; i < 4096; i += 1024) cnt[i] = 0;
-  if (threadIdx.x == 0) { s_max = 0; s_adj = 0; }
+  if (threadIdx.x == 0) { s_max = 0; s_adj = 0; s_emax = 0; s_low = 0; }
   __syncthreads();
   const long long stride = n / samples;                // >= 2 (callers guarantee n >= 65536 and samples <= n / 16)
-  unsigned adj = 0;
+  unsigned adj = 0, emax = 0;
 #pragma unroll 8
   for (int j = 0; j < samples / 1024; ++j) {
     const long long i = ((long long)j * 1024 + threadIdx.x) * stride;
     const long long g = LabelVec<LT>::one(labels, i), gn = LabelVec<LT>::one(labels, i + 1);
     atomicAdd(&cnt[((unsigned)g * 0x9E3779B1u) >> 20], 1u);
     adj += g == gn;
+    if (a) {                                           // biased exponents of the sampled values (zero / inf / NaN aside)
+      const unsigned e = (__float_as_uint(a[i]) >> 23) & 0xffu;
+      if (e != 255u) emax = max(emax, e);
+    }
+  }
+  if (a) {                                              // second look at the same samples: how many lie > 14 binades below the largest
+    emax = __reduce_max_sync(0xffffffffu, emax);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_emax, emax);
+    __syncthreads();
+    const unsigned floor_e = s_emax > 14u ? s_emax - 14u : 0u;
+    unsigned low = 0;
+    for (int j = 0; j < samples / 1024; ++j) {
+      const unsigned bits = __float_as_uint(a[((long long)j * 1024 + threadIdx.x) * stride]) & 0x7fffffffu;
+      low += bits != 0u && (bits >> 23) < floor_e;
+    }
+    low = __reduce_add_sync(0xffffffffu, low);
+    if ((threadIdx.x & 31) == 0 && low) atomicAdd(&s_low, low);
   }
   adj = __reduce_add_sync(0xffffffffu, adj);
   if ((threadIdx.x & 31) == 0 && adj) atomicAdd(&s_adj, adj);
@@ -55,6 +72,9 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
     status[4] = s_adj > (unsigned)samples / 2 ? 2 : ((s_max > (unsigned)thresh || s_adj > (unsigned)samples / 8) ? 1 : 0);
     status[5] = (int)s_max;
     status[6] = (int)s_adj;
+    // 1: more than 0.1 % of the sampled values lie below the two-word fixed-point window (16 binades, minus a margin)
+    // of the largest one: the hot-key cache then gives every slot an f64 side accumulator
+    status[7] = (a && s_low * 1024u > (unsigned)samples) ? 1 : 0;        // more than 0.1 % of the samples
   }
 }
 
@@ -104,7 +124,7 @@ inline int try_fast_pass2(const agc_request_t* r, const Tables& t, cudaStream_t 
   p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
   p.t.t0f = t.t2; p.means = t.t0f;
   p.flags = r->flags & AGC_F_NANSKIP; p.square = 0; p.want_b1 = 0; p.want_cnt = 0;
-  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size;
+  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size; p.choose2 = nullptr; p.want2 = 0;
   const bool i64 = r->index.dtype == AGC_DT_I64;
   const size_t table = (size_t)r->size * (two_word ? 8 : 4);
   // up to 12.4 K groups the means ride along in shared memory (8 more bytes per group): an LDS instead of an L2 round
@@ -164,7 +184,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   p.labels = r->index.labels; p.a = (const float*)r->a; p.n = r->n; p.size = r->size; p.t = t; p.status = r->status;
   p.flags = r->flags; p.square = op == AGC_OP_SUMSQ; p.want_b1 = want_b1;
   p.want_cnt = op == AGC_OP_MEAN || op == AGC_OP_VAR;
-  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size; p.means = nullptr; p.means_smem = 0; p.side = 0;
+  p.rshift = 0; p.nslots = 0; p.choose = nullptr; p.want = 0; p.cov = (int)r->size; p.means = nullptr; p.means_smem = 0; p.side = 0; p.choose2 = nullptr; p.want2 = 0;
   AGC_COUNT_LAUNCH(1), k_init_tables<<<(int)((r->size + 255) / 256), 256, 0, st>>>(t, r->size, r->op, r->a_dtype, r->out_dtype, 0);
   const bool i64 = r->index.dtype == AGC_DT_I64;
   int rc = 0;
@@ -278,8 +298,9 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     samples = samples < 4096 ? 4096 : (samples > PROBE_SAMPLES ? PROBE_SAMPLES : samples);
     samples &= ~1023ll;
     const int thresh = (int)(12 + samples * (PROBE_SKEW_COUNT - 12) / PROBE_SAMPLES);       // 40 at 32 Ki samples (0.1 % share), 15 at 4 Ki (0.35 %)
-    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
-    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
+    const float* pa = need_a ? (const float*)r->a : nullptr;
+    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, pa);
+    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, pa);
     AGC_COUNT_LAUNCH(1);
   }
   if (uniform_kernel == 3) {
@@ -339,9 +360,18 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   if (uniform_kernel == 0 || probe) {
     const int ctas = env_cache_ctas;
     const size_t budget = ctas == 2 ? 110 * 1024 : cap_max;     // the cache is RED-bound on its misses: capacity beats L1 here
-    p.nslots = (int)(budget / ((1 + words) * 4)) & ~1;          // even: slot s ^ 1 is the second way
+    const bool is_sum = mode == FM_SUM || mode == FM_SUMCNT;
     p.choose = probe ? choose : nullptr; p.want = 1;
-    chunked(ctas, (size_t)p.nslots * (1 + words) * 4, true);
+    // sums: with the side accumulators (8 more bytes per slot) when the probe saw values spread over more binades than the
+    // fixed-point window holds, without them (more slots, higher hit rate) for narrow data; no probe: with
+    for (int with_side = (is_sum && probe) ? 0 : (is_sum ? 1 : 0); with_side <= (is_sum ? 1 : 0) && rc >= 0; ++with_side) {
+      const size_t slot_b = (1 + words) * 4 + (with_side ? 8 : 0);
+      p.side = with_side;
+      p.nslots = (int)(budget / slot_b) & ~1;                   // even: slot s ^ 1 is the second way
+      if (is_sum && probe) { p.choose2 = r->status + 7; p.want2 = with_side; }
+      chunked(ctas, (size_t)p.nslots * slot_b, true);
+    }
+    p.choose2 = nullptr; p.side = 0;
   }
 #undef AGC_FAST_ALL
 #undef AGC_FAST_LAUNCH

@@ -59,7 +59,9 @@ struct FastParams {
   int want;
   const double* means;  // second pass of var / std: accumulate (float)((a - means[g])^2) instead of a (NULL: off)
   int means_smem;       // ... with a copy of the means in shared memory behind the table (size * 8 more bytes)
-  int side;             // k_fast sums: an f64 side accumulator per table entry (8 more bytes) takes what falls outside the fixed-point window
+  int side;             // k_fast / k_cache sums: an f64 side accumulator per table entry / slot (8 more bytes) takes what falls outside the fixed-point window
+  const int* choose2;   // k_cache: second device condition (the probe's "values span more than the window" word); run iff *choose2 == want2
+  int want2;
 };
 
 // one out-of-window value into the CTA's f64 side accumulator (shared memory, CAS loop) -- deliberately not inlined
@@ -523,6 +525,7 @@ inline int launch_maxfilter(const FastParams& p, cudaStream_t st, int sms) {
 template <int MODE, class LT, bool LOAD_A>
 __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
   if (p.choose && *p.choose != p.want) return;
+  if (p.choose2 && *p.choose2 != p.want2) return;
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
@@ -531,8 +534,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
   unsigned* w0 = sw + S;
   unsigned* w1 = sw + 2 * S;
   unsigned* w2 = sw + 3 * S;
+  // sums: an f64 side accumulator per slot for the values of a cached key that fall outside the fixed-point window -- as
+  // global REDs the out-of-window values of a HOT key queue on one L2 address (Zipf labels, data over 20 binades: 14x slower)
+  // (only when the probe saw values spread over more binades than the window: the slots it costs lower the hit rate)
+  const bool HAS_SIDE = (MODE == FM_SUM || MODE == FM_SUMCNT) && p.side;
+  unsigned* side_words = sw + (1 + WORDS) * S;               // S is even: 8-byte aligned
   const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
-  for (unsigned i = threadIdx.x; i < (1 + WORDS) * S; i += blockDim.x) sw[i] = (i >= S && i < 2 * S) ? init0 : 0u;
+  for (unsigned i = threadIdx.x; i < (1 + WORDS + (HAS_SIDE ? 2 : 0)) * S; i += blockDim.x) sw[i] = (i >= S && i < 2 * S) ? init0 : 0u;
   if (threadIdx.x == 0) s_maxbits = 0u;
   __syncthreads();
 
@@ -603,7 +611,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
       if (hit && (ab - lo_bits < span_bits)) {
         fx_add(w0 + s, w1 + s, __double2ll_rn((double)x * scale));
       } else if (ab != 0u) {
-        red_add_f64_hint(p.t.t0f + g, (double)x, pol);     // miss, or outside the exact window
+        if (hit && HAS_SIDE) smem_side_add(side_words, (int)s, (double)x);   // cached key, outside the exact window: stays on chip
+        else red_add_f64_hint(p.t.t0f + g, (double)x, pol);                   // miss (or narrow data: no side table)
       }
       if (MODE == FM_SUMCNT) {
         if (hit) atomicAdd(w2 + s, 1u);
@@ -648,7 +657,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
       }
     } else {
       long long q = (long long)(((unsigned long long)w1[s] << 32) | w0[s]);
-      if (q) atomicAdd(p.t.t0f + gi, (double)q * inv_scale);
+      const double sv = HAS_SIDE ? ((const double*)side_words)[s] : 0.0;
+      if (q != 0 || sv != 0.0) atomicAdd(p.t.t0f + gi, (double)q * inv_scale + sv);
       if (MODE == FM_SUMCNT) {
         unsigned c = w2[s];
         if (c) {

@@ -483,6 +483,27 @@ def test_len16_counter_overflow_is_forwarded_exactly():
         ac.tuning(large=1)
 
 
+@pytest.mark.parametrize("func", ["sum", "mean", "nansum", "var"])
+@pytest.mark.parametrize("binades", [4, 30])
+def test_hot_key_cache_side_accumulator(func, binades):
+    """Skewed labels on a large table (k_cache, regime 20 / 21): when the label probe also finds > 0.1 % of the sampled
+    values below the fixed-point window (status[7]), every cache slot carries an f64 side accumulator; narrow data runs
+    the layout without it.  Both must match the oracle."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(binades + len(func))
+    n, groups = (1 << 21) + 7, 100000
+    gidx = _labels(rng, n, groups, "zipf")
+    a = (np.exp2(rng.uniform(-binades / 2, binades / 2, n)) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    if "nan" in func:
+        a[rng.random(n) < 0.05] = np.nan
+    got = aggregate(gidx, a, func=func, size=groups)
+    if func != "var":
+        assert ac.last_regime() // 10 == 2, ac.last_regime()
+    with np.errstate(all="ignore"):
+        ref = oracle.aggregate(gidx, a, func=func, size=groups)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5 * float(np.nanmax(np.abs(ref[np.isfinite(ref)]))), equal_nan=True)
+
+
 @pytest.mark.parametrize("groups", [100, 5000, 12000])
 @pytest.mark.parametrize("func", ["sum", "mean", "nansum", "nanmean", "sumofsquares", "var"])
 def test_small_table_side_accumulator_for_wide_dynamic_range(func, groups):
