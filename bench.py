@@ -210,7 +210,11 @@ def run_reference(args):
 
 
 def dominant_kernel(regime):
-    fam = {0: "k_accumulate (global tables)", 1: "k_fast (shared-memory table; regime 15 = one-word carry-forwarding sums, partial table + global RED when size exceeds one SM)",
+    special = {16: "k_len16 (16-bit counters in shared memory; mean = one-word sum pass + this count pass)",
+               17: "k_maxfilter (16-bit per-group filter in shared memory + exact RED.MAX for what passes)",
+               18: "k_maxfilter (16-bit per-group filter in shared memory + exact RED.MIN for what passes)",
+               19: "k_fast (one-word carry-forwarding sum + u32 count per group)", 60: "k_accumulate_small (per-CTA shared-memory tables, any dtype)"}
+    fam = special.get(regime) or {0: "k_accumulate (global tables)", 1: "k_fast (shared-memory table; regime 15 = one-word carry-forwarding sums, partial table + global RED when size exceeds one SM)",
            2: "k_cache (per-CTA hot-key cache + global RED)", 4: "k_form3", 5: "k_runs (segmented warp reduce)"}.get(regime // 10, "?")
     return f"accumulate stage of the step: {fam}, regime {regime}"
 
