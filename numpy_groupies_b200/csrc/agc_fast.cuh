@@ -95,9 +95,13 @@ template <> struct LabelVec<int> {
 // U = 128-bit value vectors per thread per iteration: U = 1 runs 2 CTAs/SM (32 registers), U = 2 runs 1 CTA/SM with
 // twice the loads in flight per thread (tables between 110 and 226 KB, and the partial / paired modes).
 // PARTIAL: the table covers only groups [0, cov) (size too large for shared memory); the rest are global REDs.
-template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL>
+// X: the instantiation that knows about the f64 side accumulator and the second pass of var / std (p.side, p.means); the
+// plain one carries none of that code (measured: the runtime checks alone cost the 64-register variants 6 %).
+template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL, bool X>
 __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const FastParams p) {
   if (p.choose && *p.choose != p.want) return;
+  const double* const xmeans = X ? p.means : nullptr;
+  const int xside = X ? p.side : 0;
   extern __shared__ unsigned sw[];
   __shared__ unsigned s_maxbits;
   constexpr bool ONEWORD = MODE == FM_SUM1 || MODE == FM_SUMCNT1;
@@ -122,16 +126,16 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   // for narrow data, and still >100 Gelem/s when half the data takes it)
   double* side = nullptr;
   int tail_words = (WORDS * G + 1) & ~1;                   // first free (8-byte aligned) word behind the table
-  if (IS_SUM && p.side) {
+  if (IS_SUM && xside) {
     side = (double*)(sw + tail_words);
     for (int i = threadIdx.x; i < G; i += blockDim.x) side[i] = 0.0;
     tail_words += 2 * G;
   }
   const float2* mpair = nullptr;
-  if (IS_SUM && p.means && p.means_smem) {
+  if (IS_SUM && xmeans && p.means_smem) {
     float2* sm = (float2*)(sw + tail_words);
     for (int i = threadIdx.x; i < (int)p.size; i += blockDim.x) {
-      const double m = p.means[i];
+      const double m = xmeans[i];
       float2 hl; hl.x = (float)m; hl.y = (float)(m - (double)hl.x);
       sm[i] = hl;
     }
@@ -154,14 +158,14 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       int4 av = ldg_stream16((const int4*)p.a + v);
       unsigned b[4] = {(unsigned)av.x & 0x7fffffffu, (unsigned)av.y & 0x7fffffffu, (unsigned)av.z & 0x7fffffffu, (unsigned)av.w & 0x7fffffffu};
       long long gs[4] = {0, 0, 0, 0};
-      if (p.means) LabelVec<LT>::load(p.labels, v, gs);
+      if (xmeans) LabelVec<LT>::load(p.labels, v, gs);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         unsigned bb = b[k];
         if (p.square) { float f = __uint_as_float(bb); bb = __float_as_uint(f * f); }
-        if (p.means) {
+        if (xmeans) {
           const float xk = __int_as_float(k == 0 ? av.x : (k == 1 ? av.y : (k == 2 ? av.z : av.w)));
-          const double d = (gs[k] >= 0 && gs[k] < p.size) ? (double)xk - p.means[gs[k]] : 0.0;
+          const double d = (gs[k] >= 0 && gs[k] < p.size) ? (double)xk - xmeans[gs[k]] : 0.0;
           bb = __float_as_uint((float)(d * d));
         }
         if (bb < 0x7f800000u && bb > m) m = bb;
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     // Exactness is not needed here: a term as small as 2^-12 (one word) / 2^-22 (two words) of the reference is rounded
     // to the grid -- relative error of that term <= 2^-18, of the group's sum far less; only what is smaller still takes
     // the bypass
-    const int window = p.means ? (ONEWORD ? 12 : 22) : FXW;
+    const int window = xmeans ? (ONEWORD ? 12 : 22) : FXW;
     int lo_e = eb - window; if (lo_e < 1) lo_e = 1;
     lo_bits = (unsigned)lo_e << 23;
     span_bits = (unsigned)(eb - lo_e) << 23;
@@ -206,9 +210,9 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   };
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
-    if (IS_SUM && p.means) {
+    if (IS_SUM && xmeans) {
       if (mpair) { const float2 hl = mpair[g]; const float d = (x - hl.x) - hl.y; x = d * d; }
-      else { const double d = (double)x - __ldg(p.means + g); x = (float)(d * d); }
+      else { const double d = (double)x - __ldg(xmeans + g); x = (float)(d * d); }
     }
     if (PARTIAL && g >= p.cov) { direct_global(g, x); return; }
     const int gi = ((int)g << rs) | rsel;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       } else if (ab != 0u) {                        // out of window (huge / tiny / inf / NaN): f64, on chip if there is room
         // (the side table's address is recomputed from the kernel parameters and the add is an out-of-line call: the hot
         // loop of the 32-register variant has no room for another live pointer)
-        if (p.side) smem_side_add(sw + ((WORDS * (p.cov << p.rshift) + 1) & ~1), gi, (double)x);
+        if (xside) smem_side_add(sw + ((WORDS * (p.cov << p.rshift) + 1) & ~1), gi, (double)x);
         else atomicAdd(p.t.t0f + g, (double)x);
       }
       if (HAS_CNT) atomicAdd(wc + gi, 1u);
@@ -682,9 +686,9 @@ inline int launch_cache(const FastParams& p, int ctas_per_sm, size_t smem, cudaS
   return 1;
 }
 
-template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL>
-inline int launch_fast_u(const FastParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = k_fast<MODE, LT, LOAD_A, U, PARTIAL>;
+template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL, bool X>
+inline int launch_fast_x(const FastParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = k_fast<MODE, LT, LOAD_A, U, PARTIAL, X>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
@@ -692,6 +696,14 @@ inline int launch_fast_u(const FastParams& p, int grid, size_t smem, cudaStream_
   }
   AGC_COUNT_LAUNCH(1), kern<<<grid, FAST_THREADS, smem, st>>>(p);
   return 1;
+}
+template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL>
+inline int launch_fast_u(const FastParams& p, int grid, size_t smem, cudaStream_t st) {
+  constexpr bool SUMMODE = MODE == FM_SUM || MODE == FM_SUMCNT || MODE == FM_SUM1 || MODE == FM_SUMCNT1;
+  if constexpr (SUMMODE && LOAD_A && !PARTIAL) {
+    if (p.side || p.means) return launch_fast_x<MODE, LT, LOAD_A, U, PARTIAL, true>(p, grid, smem, st);
+  }
+  return launch_fast_x<MODE, LT, LOAD_A, U, PARTIAL, false>(p, grid, smem, st);
 }
 template <int MODE, class LT, bool LOAD_A>
 inline int launch_fast(const FastParams& p, int ctas_per_sm, size_t smem, cudaStream_t st, int sms) {
