@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
     __syncthreads();
     const unsigned floor_e = s_emax > 14u ? s_emax - 14u : 0u;
     unsigned low = 0;
+#pragma unroll 8
     for (int j = 0; j < samples / 1024; ++j) {
       const unsigned bits = __float_as_uint(a[((long long)j * 1024 + threadIdx.x) * stride]) & 0x7fffffffu;
       low += bits != 0u && (bits >> 23) < floor_e;
