@@ -61,6 +61,26 @@ def test_fast_path_is_taken_and_matches_general_path(labels_dtype):
             np.testing.assert_allclose(fast, slow, rtol=1e-6)
 
 
+@pytest.mark.parametrize("dist", ["uniform", "zipf", "sorted"])
+@pytest.mark.parametrize("groups", [20000, 100000])
+def test_int32_labels_on_the_large_table_kernels(groups, dist):
+    """The int32-label instantiations of the one-word sum / count / filter / hot-key-cache / run kernels."""
+    rng = np.random.default_rng(groups + len(dist))
+    n = (1 << 21) + 2
+    gidx = _labels(rng, n, groups, dist).astype(np.int32)
+    a = rng.standard_normal(n).astype(np.float32)
+    a[rng.random(n) < 0.03] = np.nan
+    for func in ("sum", "nansum", "mean", "nanmean", "max", "nanmin", "len", "nanlen", "var"):
+        got = aggregate(gidx, a, func=func, size=groups, fill_value=-1)
+        with np.errstate(all="ignore"):
+            ref = oracle.aggregate(gidx, a, func=func, size=groups, fill_value=-1)
+        assert got.dtype == ref.dtype, func
+        if func in ("max", "nanmin", "len", "nanlen"):
+            np.testing.assert_array_equal(got, ref, err_msg=func)
+        else:
+            np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5 * float(np.nanmax(np.abs(ref[np.isfinite(ref)]))), equal_nan=True, err_msg=func)
+
+
 def test_fixed_point_sum_is_exact_for_dyadic_data():
     """torch.rand-style values k*2^-24 convert exactly into the fixed-point window, so the fast sum equals
     the exactly-rounded result: compare against an integer sum."""
