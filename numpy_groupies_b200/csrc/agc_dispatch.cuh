@@ -1,14 +1,22 @@
-// agc_dispatch.cuh -- which accumulate kernel runs: the device-side label probe and try_fast_path().
+// agc_dispatch.cuh -- which accumulate kernel runs: the device-side label probe, try_fast_path() and try_fast_pass2().
 //
-//   table fits one SM's shared memory ............ k_fast (agc_fast.cuh), replicated when small
-//   Form 3 on the last axis ...................... k_form3 (agc_form3.cuh)
-//   larger tables (no host round trip: the probe writes status[4], every candidate kernel is launched and the ones
-//   that were not chosen return at once)
+// Form 1, f32 values, int32 / int64 labels, sum / sumofsquares / mean / var / min / max / len (+ nan-forms):
+//   table <= 195 KB of shared memory per SM ...... k_fast (agc_fast.cuh): whole table per CTA, replicated when small, two
+//       (AGC_SMEM1 / AGC_SMEM2: more than 196 KB     CTAs per SM up to 97 KB each; sums of <= 12.4 K groups carry an f64 side
+//        per SM costs a third of the load bandwidth)  accumulator; mean / var on 16.6 K - 24.9 K groups: one-word sum + count
+//   larger tables (no host round trip: the probe writes status[4] -- 0 uniform, 1 skewed, 2 runs -- and status[7] -- values
+//   spread beyond the fixed-point window --, every candidate kernel is launched and the ones not chosen return at once)
 //       labels in runs (sorted / contiguous) ..... k_runs  (agc_runs.cuh): segmented warp reduce
-//       skewed labels ............................ k_cache (agc_fast.cuh): per-CTA hot-key cache + global RED
-//       otherwise ................................ k_fast partial table + global RED; plain sums in the one-word
-//                                                  carry-forwarding format, mean / var as sum pass + count pass
-//   everything else .............................. k_accumulate (agc_generic.cuh)
+//       skewed labels ............................ k_cache (agc_fast.cuh): per-CTA hot-key cache + global RED (max / min up to
+//                                                  113 K groups: k_maxfilter over the whole table, with the exact test on ties)
+//       otherwise: sum ........................... k_fast one-word carry-forwarding sums, partial table + global RED
+//                  max / min ..................... k_maxfilter: 16-bit per-group filter + exact RED for what passes
+//                  len ........................... k_len16: 16-bit counters, read-check-repair overflow forwarding
+//                  mean / var pass 1 ............. one-word sum pass + count pass (k_len16)
+//       partial tables take 195 KB while that covers >= 90 % of the groups, else 226 KB (pick_cov)
+//   second pass of var / std, f32 result ......... k_fast on (float)((a - mean)^2) up to 49.9 K groups (try_fast_pass2)
+// Form 3 on the last axis .......................... k_form3 (agc_form3.cuh)
+// everything else .................................. k_accumulate_small (<= 16.5 K groups) / k_accumulate (agc_small / agc_generic)
 #pragma once
 #include "agc_fast.cuh"
 #include "agc_form3.cuh"
