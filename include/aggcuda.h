@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AGC_ABI_VERSION 3
+#define AGC_ABI_VERSION 4
 
 /* element dtypes (values, labels and outputs) */
 enum {
@@ -59,7 +59,10 @@ enum {
   AGC_OP_CUMMAX = 18,  /* aggregate_numba.py CumMax  :495-496 */
   AGC_OP_CUMMIN = 19,  /* aggregate_numba.py CumMin  :499-500 */
   AGC_OP_SORT = 20,    /* _sort :210-214 (AGC_F_REVERSE for reverse=True) */
-  AGC_OP_COUNT = 21
+  /* fused multi-statistic accumulation (README.md:185 "min+max in one pass"): only with AGC_F_ACC_ONLY; leaves max keys in
+   * T0 and min keys in T2, which AGC_F_FIN_ONLY calls with op = MAX / op = MIN | AGC_F_KEYS_IN_T2 turn into results */
+  AGC_OP_MINMAX = 21,
+  AGC_OP_COUNT = 22
 };
 
 /* request flags */
@@ -75,6 +78,9 @@ enum {
 #define AGC_F_NO_INIT        0x0200  /* with ACC_ONLY: do not re-initialise tables (accumulate more shards)   */
 #define AGC_F_PASS2          0x0400  /* with ACC_ONLY: run only the second pass of var/std/arg* over tables   */
                                      /* the caller has merged (multi-GPU: sum,count / extreme key)            */
+#define AGC_F_TOUCHED_BY_COUNT 0x0800 /* FIN_ONLY of sum over tables a mean / var pass left: touched = count > 0 */
+#define AGC_F_KEYS_IN_T2     0x1000  /* FIN_ONLY of min after AGC_OP_MINMAX: the min keys live in T2            */
+#define AGC_F_DETERMINISTIC  0x2000  /* float sums in a fixed order: same bits for any kernel schedule / GPU count */
 
 /* how the flat group of element i is obtained (input_validation's three shapes, utils.py:435-542) */
 enum {
@@ -150,6 +156,22 @@ int64_t     agc_group_order_workspace_bytes(int64_t n, int64_t size);
 int         agc_group_order(const agc_index_t* index, int64_t n, int64_t size, int64_t* order, int64_t* offsets,
                             void* workspace, int64_t workspace_bytes, int32_t* status, void* stream);
 
+/* ---- label utilities (the steps either side of aggregate): one chained single-pass scan over int64 ----
+ * mode 0 step_indices (aggregate_numba.py:591-605): out = int64[total + 1] run starts of x followed by n
+ *      1 step_count   (aggregate_numba.py:577-588): only *total = number of runs
+ *      2 label_contiguous_1d (utils.py:597-632): out = int64[n]; x bool mask or integer values
+ *      3 relabel table of relabel_groups_masked (utils.py:651-681): x = keep flags (size entries), out[k] = new label of k
+ *        in integer dtype out_dtype
+ *      4 inclusive running sum of the integers x into int64 out (multi_arange, utils.py:572-594)
+ * `total` (device int64, may be NULL) receives the sum of all per-element flags / values. */
+int64_t     agc_label_scan_workspace_bytes(int64_t n);
+int         agc_label_scan(int32_t mode, const void* x, int32_t x_dtype, int64_t n, void* out, int32_t out_dtype,
+                           int64_t* total, void* workspace, int64_t workspace_bytes, void* stream);
+/* keep[g] = 1 for every label g that occurs (keep is uint8[size], zeroed by the caller): relabel_groups_unique, utils.py:635-648 */
+int         agc_mark_present(const void* labels, int32_t dtype, int64_t n, int64_t size, void* keep, int32_t* status, void* stream);
+/* multi_arange (utils.py:572-594): incl = inclusive running sums of n (int64[m]), out = int64[total] */
+int         agc_multi_arange(const int64_t* incl, int64_t m, int64_t total, int64_t* out, void* stream);
+
 /* measurement hooks (bench.py): when enabled, agc_aggregate brackets its dominant accumulate kernel with
  * CUDA events on the caller's stream; agc_profile_last_ms() waits for that kernel and returns its duration.
  * agc_launch_count() = number of libaggcuda kernels launched by this process so far. */
@@ -165,7 +187,9 @@ int64_t     agc_launch_count(void);
  *          of L1 for the global loads in flight; the 228 KB carve-out costs a third of the streaming bandwidth)
  *   key 4  the same per CTA for kernels that run two CTAs per SM (default 99200)
  *   key 5  a partial table keeps the key-3 size while at most this percentage of the groups stays uncovered; beyond
- *          that it grows to the full 226 KB (default 10) */
+ *          that it grows to the full 226 KB (default 10)
+ *   key 6  sorted-label scans: 1 single-pass chained scan with warp-parallel look-back (default), 0 the three-kernel
+ *          reduce / scan-tiles / apply variant */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus

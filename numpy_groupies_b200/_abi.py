@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaggcuda.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_NDIM = 8
 
 # ---- enums (mirror include/aggcuda.h) ----------------------------------------------------------
@@ -16,9 +16,11 @@ DT = {"bool": 0, "int8": 1, "uint8": 2, "int16": 3, "uint16": 4, "int32": 5, "ui
 DT_NAME = {v: k for k, v in DT.items()}
 OP = {"sum": 0, "prod": 1, "len": 2, "last": 3, "first": 4, "all": 5, "any": 6, "min": 7, "max": 8, "argmax": 9,
       "argmin": 10, "mean": 11, "sumofsquares": 12, "var": 13, "std": 13, "allnan": 14, "anynan": 15,
-      "cumsum": 16, "cumprod": 17, "cummax": 18, "cummin": 19, "sort": 20}
+      "cumsum": 16, "cumprod": 17, "cummax": 18, "cummin": 19, "sort": 20, "minmax": 21}
 F_NANSKIP, F_SQRT, F_REVERSE, F_ASSUME_SORTED, F_NO_FAST = 0x1, 0x2, 0x4, 0x8, 0x10
 F_NEED_TOUCHED, F_ACC_ONLY, F_FIN_ONLY, F_FILL_NAN, F_NO_INIT, F_PASS2 = 0x20, 0x40, 0x80, 0x100, 0x200, 0x400
+F_TOUCHED_BY_COUNT, F_KEYS_IN_T2, F_DETERMINISTIC = 0x800, 0x1000, 0x2000
+LB_STEPS, LB_STEP_COUNT, LB_CONTIG, LB_KEEP, LB_CUMSUM = 0, 1, 2, 3, 4
 FORM_FLAT, FORM_AXIS, FORM_MULTI = 0, 1, 2
 ST_BADLABEL, ST_PRECISION, ST_UNSORTED, ST_REGIME = 0, 1, 2, 3
 REDUCE_NAMES = {0: "sum", 1: "max", 2: "min", 3: "prod"}
@@ -45,7 +47,8 @@ class Partial(C.Structure):
 
 EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_partials", "agc_aggregate",
            "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order",
-           "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count", "agc_tuning")
+           "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count", "agc_tuning",
+           "agc_label_scan_workspace_bytes", "agc_label_scan", "agc_mark_present", "agc_multi_arange")
 
 _lib = None
 
@@ -81,6 +84,15 @@ def load():
     lib.agc_group_order.restype = C.c_int
     lib.agc_group_order.argtypes = [C.POINTER(Index), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_void_p]
+    lib.agc_label_scan_workspace_bytes.restype = C.c_int64
+    lib.agc_label_scan_workspace_bytes.argtypes = [C.c_int64]
+    lib.agc_label_scan.restype = C.c_int
+    lib.agc_label_scan.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p]
+    lib.agc_mark_present.restype = C.c_int
+    lib.agc_mark_present.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.agc_multi_arange.restype = C.c_int
+    lib.agc_multi_arange.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.agc_profile_enable.restype = C.c_int
     lib.agc_profile_enable.argtypes = [C.c_int]
     lib.agc_profile_last_ms.restype = C.c_float

@@ -28,7 +28,8 @@ import numpy as np
 
 from . import _abi, _semantics as sem
 
-__all__ = ["aggregate", "unpack"]
+__all__ = ["aggregate", "unpack", "uaggregate", "aggregate_multi", "group_csr", "step_count", "step_indices",
+           "label_contiguous_1d", "relabel_groups_masked", "relabel_groups_unique", "multi_arange", "is_duck_array"]
 
 _torch = None
 
@@ -43,10 +44,10 @@ def last_regime():
     return _LAST["regime"]
 
 
-def tuning(large=-1, cache_ctas=-1, sum1=-1, smem1=-1, smem2=-1, uncov_pct=-1):
+def tuning(large=-1, cache_ctas=-1, sum1=-1, smem1=-1, smem2=-1, uncov_pct=-1, scan_chain=-1):
     """Kernel-selection knobs of libaggcuda (agc_tuning, include/aggcuda.h): for tests and A/B measurements."""
     lib = _abi.load()
-    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1, smem1, smem2, uncov_pct)))
+    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1, smem1, smem2, uncov_pct, scan_chain)))
 
 
 def _t():
@@ -121,13 +122,70 @@ def _tensor_np_dtype(t):
         return dt
 
 
+_STAGE = {"bufs": None, "pool": None, "events": None}
+_STAGE_CHUNK = 32 << 20          # bytes per pinned staging buffer
+_STAGE_BUFS = 3
+_STAGE_THREADS = 4
+
+
+def _stage_setup():
+    torch = _t()
+    if _STAGE["bufs"] is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _STAGE["bufs"] = [torch.empty(_STAGE_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(_STAGE_BUFS)]
+        _STAGE["events"] = [None] * _STAGE_BUFS
+        _STAGE["pool"] = ThreadPoolExecutor(max_workers=_STAGE_THREADS)
+    return _STAGE
+
+
+def _upload_staged(src_u8, dst_u8):
+    """Pageable host bytes -> device at close to PCIe rate: a ring of pinned staging buffers, filled by a few host
+    threads (numpy's memcpy releases the GIL) while the previous chunk's asynchronous H2D copy is in flight.
+    (A plain copy from pageable memory runs at ~14 GB/s: the driver stages it through one small buffer, single-threaded.)"""
+    torch = _t()
+    st = _stage_setup()
+    bufs, events, pool = st["bufs"], st["events"], st["pool"]
+    n = src_u8.shape[0]
+    k = 0
+    for off in range(0, n, _STAGE_CHUNK):
+        m = min(_STAGE_CHUNK, n - off)
+        i = k % _STAGE_BUFS
+        if events[i] is not None:
+            events[i].synchronize()                        # the copy that last read this buffer is done
+        stage = bufs[i].numpy()
+        step = -(-m // _STAGE_THREADS)
+        futs = [pool.submit(np.copyto, stage[j:min(j + step, m)], src_u8[off + j:off + min(j + step, m)]) for j in range(0, m, step)]
+        for f in futs:
+            f.result()
+        dst_u8[off:off + m].copy_(bufs[i][:m], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        events[i] = ev
+        k += 1
+
+
 def _upload(arr, device):
-    """numpy array -> contiguous device buffer (H2D copy)."""
+    """numpy array -> contiguous device buffer (H2D copy).  Page-locked arrays (e.g. ``torch.empty(..., pin_memory=True)
+    .numpy()``) go as one asynchronous DMA; large pageable arrays through the pinned staging ring; small ones directly."""
     torch = _t()
     arr = np.ascontiguousarray(arr)
     dt = arr.dtype
     view = arr.view(_SIGNED_VIEW[dt.name]) if dt.name in _SIGNED_VIEW else arr
-    return _Dev(torch.from_numpy(view).to(device, non_blocking=False), dt)
+    if not view.flags.writeable:                            # torch.from_numpy warns on read-only memory; we never write
+        view = view.view()
+        try:
+            view.flags.writeable = True
+        except ValueError:
+            view = np.array(view)
+    t = torch.from_numpy(view)
+    if view.nbytes >= (8 << 20):
+        if t.is_pinned():
+            return _Dev(t.to(device, non_blocking=True), dt)
+        with torch.cuda.device(device):
+            out = torch.empty(t.shape, dtype=t.dtype, device=device)
+            _upload_staged(view.reshape(-1).view(np.uint8), out.reshape(-1).view(torch.uint8))
+        return _Dev(out, dt)
+    return _Dev(t.to(device, non_blocking=False), dt)
 
 
 def _from_tensor(t):
@@ -553,18 +611,12 @@ def _run_array(c):
     vals = _host_values(c)
     order, offsets = order.cpu().numpy(), offsets.cpu().numpy()
     pieces = np.split(vals[order], offsets[1:-1])
-    ret = np.asanyarray(pieces, dtype="object") if len(pieces) != 1 else _one_group_object(pieces)
+    ret = np.asanyarray(pieces, dtype="object")
     fill = c.fill_value
     if fill is None or np.isscalar(fill):
         counts = np.diff(offsets)
         ret[counts == 0] = fill
     return ret
-
-
-def _one_group_object(pieces):
-    ret = np.empty(1, dtype=object)
-    ret[0] = pieces[0]
-    return np.asanyarray(pieces, dtype="object")
 
 
 def _run_callable(c):
@@ -603,27 +655,41 @@ def aggregate(group_idx, a, func="sum", size=None, fill_value=0, order="C", dtyp
     return _finish_shape_np(c, ret)
 
 
-def unpack(group_idx, ret):
-    """``ret[group_idx]`` on the device (utils.py:548-553)."""
+def _unpack_dev(lab, tab):
+    """agc_unpack on device buffers: tab[lab] as a new _Dev of tab's dtype."""
     torch = _require_cuda()
     lib = _abi.load()
-    device_mode = _is_tensor(group_idx) or _is_tensor(ret)
-    device = (group_idx.device if _is_tensor(group_idx) else ret.device) if device_mode else torch.device("cuda", torch.cuda.current_device())
-    lab = _from_tensor(group_idx) if _is_tensor(group_idx) else _upload(np.asanyarray(group_idx), device)
-    tab = _from_tensor(ret) if _is_tensor(ret) else _upload(np.asanyarray(ret), device)
+    device = lab.t.device
     n = lab.t.numel()
-    out = _empty(n, tab.dtype, device)
-    status = torch.zeros(8, dtype=torch.int32, device=device)
     with torch.cuda.device(device):
+        out = _empty(n, tab.dtype, device)
+        status = torch.zeros(8, dtype=torch.int32, device=device)
         rc = lib.agc_unpack(tab.ptr, tab.dtype.itemsize, tab.t.numel(), lab.ptr, _abi.dtype_code(lab.dtype), n,
                             out.ptr, status.data_ptr(), _stream_ptr(device))
         if rc:
             raise RuntimeError(_abi.last_error())
-        if status.cpu().numpy()[_abi.ST_BADLABEL]:
+        if n and status.cpu().numpy()[_abi.ST_BADLABEL]:
             raise IndexError("index out of bounds in unpack")
+    return out
+
+
+def unpack(group_idx, ret):
+    """``ret[group_idx]`` on the device (utils.py:548-553): the packed per-group result broadcast back to the elements."""
+    torch = _require_cuda()
+    device_mode = _is_tensor(group_idx) or _is_tensor(ret)
     if device_mode:
-        return _as_user_tensor(out).reshape(tuple(group_idx.shape))
-    return _download(out).reshape(np.shape(group_idx))
+        device = next(x.device for x in (group_idx, ret) if _is_tensor(x) and x.is_cuda)
+    else:
+        device = torch.device("cuda", torch.cuda.current_device())
+    lab = _as_device_ints(group_idx, device)
+    tab = _from_tensor(ret if ret.is_cuda else ret.to(device)) if _is_tensor(ret) else _upload(np.asanyarray(ret), device)
+    if lab.dtype.kind not in "iu":
+        raise IndexError("arrays used as indices must be of integer type")
+    out = _unpack_dev(lab, tab)
+    shape = tuple(group_idx.shape) if hasattr(group_idx, "shape") else np.shape(group_idx)
+    if device_mode:
+        return _as_user_tensor(out).reshape(shape)
+    return _download(out).reshape(shape)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -644,3 +710,324 @@ def _plan_only_for_tests(group_idx, a, func="sum", size=None, fill_value=0, orde
         else:
             sem.finish_multi_plan(plan, [int(v) + 1 for v in g.max(axis=1)])
     return _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, dict(kwargs), resolve_on_host)
+
+
+# ------------------------------------------------------------------------------------------------
+# the callers either side of the path: uaggregate, fused multi-statistic aggregation,
+# device-side grouping (CSR) for `array` / generic callables, label utilities
+# ------------------------------------------------------------------------------------------------
+def uaggregate(group_idx, a, **kwargs):
+    """``unpack(group_idx, aggregate(group_idx, a, **kwargs))`` (numpy_groupies/__init__.py:42-43): the per-group
+    result broadcast back to the elements.  Device tensors stay on the device between the two steps."""
+    return unpack(group_idx, aggregate(group_idx, a, **kwargs))
+
+
+# func -> (family, what the finalise step is asked for).  One accumulate pass per family serves all its members.
+_MOMENTS = {"sum": "sum", "len": "len", "mean": "mean", "var": "var", "std": "std"}
+_EXTREMES = {"min", "max"}
+
+
+def aggregate_multi(group_idx, a, funcs, size=None, fill_value=0, order="C", dtype=None, axis=None, **kwargs):
+    """Several statistics of the same ``(group_idx, a)`` from as few passes over the data as possible -- the fused
+    aggregation the reference's README (:185, "min+max in one pass") names as the missed optimisation.
+
+    ``funcs`` is a sequence of function names; the result is a dict ``{name: array}`` whose entries equal
+    ``aggregate(group_idx, a, name, size=..., fill_value=..., ...)`` one by one.  Fused families:
+      * sum / len / mean / var / std (and their nan-forms, as a family of their own) on floating ``a``: ONE accumulate
+        pass leaves (sum, count) per group, var / std add the reference's second pass (aggregate_numpy.py:180-187);
+        every member is just another finalise over the same tables;
+      * min + max: one pass that feeds both key tables (AGC_OP_MINMAX).
+    Everything else, integer ``a`` for sum (its accumulator is an exact int64) and ``dtype=`` overrides run as separate
+    calls.  ``size`` should be given: with ``size=None`` every member would measure the labels again.
+    """
+    names = [sem.canonical_func(f) for f in funcs]
+    if any(not isinstance(nm, str) for nm in names):
+        raise TypeError("aggregate_multi takes function names")
+    out = {}
+    todo = list(dict.fromkeys(names))
+    ddof = kwargs.get("ddof", 0)
+    plain_kwargs = {k: v for k, v in kwargs.items() if k != "ddof"}
+
+    def single(nm):
+        kw = dict(plain_kwargs)
+        if nm.replace("nan", "", 1) in ("var", "std"):
+            kw["ddof"] = ddof
+        return aggregate(group_idx, a, nm, size=size, fill_value=fill_value, order=order, dtype=dtype, axis=axis, **kw)
+
+    a_is_float = (np.issubdtype(_tensor_np_dtype(a), np.floating) if _is_tensor(a)
+                  else np.issubdtype(np.asanyarray(a).dtype, np.floating)) if not isinstance(a, (int, float)) else False
+    for nan_form in (False, True):
+        pre = "nan" if nan_form else ""
+        mom = [nm for nm in todo if nm.startswith(pre) and nm[len(pre):] in _MOMENTS and (nan_form or not nm.startswith("nan"))]
+        if len(mom) >= 2 and a_is_float and dtype is None and size is not None:
+            for nm, res in _fused_family(group_idx, a, mom, "moments", size, fill_value, order, axis, ddof, plain_kwargs).items():
+                out[nm] = res
+        ext = [nm for nm in todo if nm.startswith(pre) and nm[len(pre):] in _EXTREMES and (nan_form or not nm.startswith("nan"))]
+        if len(ext) == 2 and dtype is None and size is not None:
+            for nm, res in _fused_family(group_idx, a, ext, "extremes", size, fill_value, order, axis, ddof, plain_kwargs).items():
+                out[nm] = res
+    for nm in todo:
+        if nm not in out:
+            out[nm] = single(nm)
+    return {nm: out[nm] for nm in names}
+
+
+def _fused_family(group_idx, a, members, family, size, fill_value, order, axis, ddof, kwargs):
+    """One accumulate pass (two for var / std), one finalise per member.  Every member is planned by the same host
+    code as a single call (dtype, fill and error rules are the reference's), only the kernels are shared."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    calls = {}
+    for nm in members:
+        kw = dict(kwargs)
+        if nm.replace("nan", "", 1) in ("var", "std"):
+            kw["ddof"] = ddof
+        calls[nm] = _prepare(group_idx, a, nm, size, fill_value, order, None, axis, kw, _resolve_size_device)
+    c0 = calls[members[0]]
+    device = _device_of(c0)
+    lab = _labels_on_device(c0, device)
+    vals = _values_on_device(c0, device)
+    plan = c0.plan
+    if vals is None:
+        raise ValueError("aggregate_multi needs an array a")
+    bases = {nm: c.base for nm, c in calls.items()}
+    need_pass2 = any(b in ("var", "std") for b in bases.values())
+    if family == "moments":
+        acc_op = "var" if need_pass2 else "mean"
+    else:
+        acc_op = "minmax"
+
+    results = {}
+    with torch.cuda.device(device):
+        status = torch.zeros(8, dtype=torch.int32, device=device)
+        stream = _stream_ptr(device)
+        req = _abi.Request()
+        a_dt = np.dtype(_COMPUTE_AS.get(_dtname(c0.a_dtype), c0.a_dtype))
+        req.a_dtype = _abi.dtype_code(a_dt)
+        req.a = vals.ptr
+        req.index = _build_index(c0, lab)
+        req.n, req.size = plan.n, plan.flat_size
+        req.index_base = 0
+        req.arg_stride, req.arg_len = plan.arg_stride, plan.arg_len
+        req.status = status.data_ptr()
+        nan_flag = _abi.F_NANSKIP if c0.nan_form else 0
+
+        def call(op, flags, c=None, out=None):
+            req.op = _abi.OP[op]
+            req.flags = flags
+            cc = c or c0
+            compute_out = np.dtype(_COMPUTE_AS.get(_dtname(cc.out_dtype), cc.out_dtype))
+            req.out_dtype = _abi.dtype_code(compute_out)
+            req.fill_f64, req.fill_i64, _ = _fill_numbers(cc.fill_value, compute_out)
+            req.ddof = float(getattr(cc, "ddof", 0))
+            req.out = out.ptr if out is not None else 0
+            rc = lib.agc_aggregate(C.byref(req), stream)
+            if rc:
+                raise RuntimeError(f"agc_aggregate failed ({rc}): {_abi.last_error()}")
+
+        # workspace: the reduction layout does not depend on the op
+        req.op, req.flags, req.out_dtype, req.out = _abi.OP["mean"], 0, _abi.dtype_code(np.dtype(np.float64)), 0
+        ws_bytes = lib.agc_workspace_bytes(C.byref(req))
+        if ws_bytes < 0:
+            raise RuntimeError(_abi.last_error())
+        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
+        req.workspace, req.workspace_bytes = ws.data_ptr(), ws_bytes
+
+        base_flags = nan_flag | (0 if c0.fast else _abi.F_NO_FAST)
+        call(acc_op, base_flags | _abi.F_ACC_ONLY)                       # pass 1: (sum, count) or both key tables
+
+        def finish(nm):
+            c = calls[nm]
+            compute_out = np.dtype(_COMPUTE_AS.get(_dtname(c.out_dtype), c.out_dtype))
+            o = _empty(plan.flat_size, compute_out, device)
+            flags = c.flags | _abi.F_FIN_ONLY
+            if family == "moments" and c.base == "sum":
+                flags |= _abi.F_TOUCHED_BY_COUNT
+            if family == "extremes" and c.base == "min":
+                flags |= _abi.F_KEYS_IN_T2
+            call(c.base, flags, c, o)
+            if c.out_dtype != compute_out:
+                o = _Dev(o.t.to(getattr(torch, c.out_dtype.name)), c.out_dtype)
+            return o
+
+        first = [nm for nm in members if bases[nm] not in ("var", "std")]
+        for nm in first:                                                 # sum / len / mean read the pass-1 tables
+            results[nm] = finish(nm)
+        if need_pass2:                                                   # then T0 turns into the means and pass 2 runs
+            call("var", base_flags | _abi.F_ACC_ONLY | _abi.F_PASS2 | _abi.F_NO_INIT)
+            for nm in members:
+                if bases[nm] in ("var", "std"):
+                    results[nm] = finish(nm)
+        if c0.check:
+            st = status.cpu().numpy()
+            if st[_abi.ST_BADLABEL]:
+                raise ValueError("group_idx contains negative indices or indices too large for size")
+    final = {}
+    for nm, o in results.items():
+        c = calls[nm]
+        if c.device_mode:
+            res = _finish_shape_torch(c, _as_user_tensor(o))
+            final[nm] = res.cpu() if c.return_cpu else res
+        else:
+            final[nm] = _finish_shape_np(c, _download(o))
+    return final
+
+
+def group_csr(group_idx, a=None, size=None, order="C", axis=None, check=True):
+    """Device-side grouping for ``func='array'`` / arbitrary callables (aggregate_numpy.py:217-241,
+    aggregate_numba.py:228-291) WITHOUT the trip through Python objects: a stable radix sort of the element positions
+    by flat group.  Returns ``(order, offsets, values)`` as CUDA tensors: ``order[offsets[g]:offsets[g+1]]`` are the
+    positions of group ``g`` in their original order, ``values = a.ravel()[order]`` (``None`` when ``a`` is None) --
+    i.e. a CSR layout any device-side per-group function can walk."""
+    torch = _require_cuda()
+    probe = a if a is not None else 0
+    c = _prepare(group_idx, probe, "array", size, 0, order, None, axis, {"check": check}, _resolve_size_device)
+    order_t, offsets_t = _group_order(c)
+    values = None
+    if a is not None and not c.a_scalar:
+        dev = _values_on_device(c, _device_of(c))
+        values = _as_user_tensor(_unpack_dev(_Dev(order_t, np.int64), dev))
+    return order_t, offsets_t, values
+
+
+def _as_device_ints(x, device):
+    if _is_tensor(x):
+        return _from_tensor(x if x.is_cuda else x.to(device))
+    arr = np.asanyarray(x)
+    return _upload(arr, device)
+
+
+def _label_scan(mode, x, out_dtype=np.int64, out_len=None, want_total=False):
+    """agc_label_scan on a device buffer ``x`` (a _Dev): returns (out _Dev | None, total int | None)."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    device = x.t.device
+    n = x.t.numel()
+    with torch.cuda.device(device):
+        out = _empty(out_len if out_len is not None else n, out_dtype, device) if mode != _abi.LB_STEP_COUNT else None
+        total = torch.zeros(1, dtype=torch.int64, device=device)
+        ws_bytes = lib.agc_label_scan_workspace_bytes(n)
+        ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
+        rc = lib.agc_label_scan(mode, x.ptr, _abi.dtype_code(x.dtype), n, out.ptr if out is not None else 0,
+                                _abi.dtype_code(np.dtype(out_dtype)), total.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(device))
+        if rc:
+            raise RuntimeError(_abi.last_error())
+        tot = int(total.item()) if want_total else None
+    return out, tot
+
+
+def _check_int_1d(x, what):
+    nd = x.ndim if hasattr(x, "ndim") else np.ndim(x)
+    if nd != 1:
+        raise ValueError(f"{what} is supposed to be 1d array.")
+
+
+def _finish_like(x, dev):
+    return _as_user_tensor(dev) if _is_tensor(x) else _download(dev)
+
+
+def step_count(group_idx):
+    """Number of runs of equal labels in ``group_idx`` (aggregate_numba.py:577-588), counted on the device."""
+    torch = _require_cuda()
+    device = group_idx.device if _is_tensor(group_idx) and group_idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x = _as_device_ints(group_idx, device)
+    if x.t.numel() == 0:
+        return 0
+    return _label_scan(_abi.LB_STEP_COUNT, x, want_total=True)[1]
+
+
+def step_indices(group_idx):
+    """Edges of the runs of equal labels (aggregate_numba.py:591-605): ``[0, ..., len(group_idx)]``."""
+    torch = _require_cuda()
+    device = group_idx.device if _is_tensor(group_idx) and group_idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x = _as_device_ints(group_idx, device)
+    n = x.t.numel()
+    if n == 0:
+        # the reference writes indices[0] = 0 and indices[-1] = size into a one-element array
+        return _finish_like(group_idx, _upload(np.zeros(1, dtype=np.int64), device))
+    out, total = _label_scan(_abi.LB_STEPS, x, out_len=n + 1, want_total=True)
+    out.t = out.t[:total + 1]
+    return _finish_like(group_idx, out)
+
+
+def label_contiguous_1d(X):
+    """Label contiguous blocks of a 1-d mask / of equal non-zero values with 1, 2, 3 ... (utils.py:597-632)."""
+    torch = _require_cuda()
+    _check_int_1d(X, "this")
+    device = X.device if _is_tensor(X) and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x = _as_device_ints(X, device)
+    if x.dtype.kind not in "biu":
+        raise NotImplementedError("label_contiguous_1d on the device takes bool or integer input")
+    out, _ = _label_scan(_abi.LB_CONTIG, x)
+    return _finish_like(X, out)
+
+
+def _relabel(g, keep, like):
+    table, _ = _label_scan(_abi.LB_KEEP, keep, out_dtype=g.dtype)          # table[k] = new number of group k (0 if removed)
+    return _finish_like(like, _unpack_dev(g, table))
+
+
+def relabel_groups_masked(group_idx, keep_group):
+    """Remove the groups whose ``keep_group`` entry is falsy and renumber the rest without gaps (utils.py:651-681)."""
+    torch = _require_cuda()
+    device = group_idx.device if _is_tensor(group_idx) and group_idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    g = _as_device_ints(group_idx, device)
+    if _is_tensor(keep_group):
+        k = _as_device_ints(keep_group, device)
+    else:
+        k = _upload(np.asanyarray(keep_group).astype(bool), device)
+    return _relabel(g, k, group_idx)
+
+
+def relabel_groups_unique(group_idx):
+    """Renumber the labels that actually occur (plus group 0) without gaps, keeping their order (utils.py:635-648)."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    device = group_idx.device if _is_tensor(group_idx) and group_idx.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    g = _as_device_ints(group_idx, device)
+    n = g.t.numel()
+    if n == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    with torch.cuda.device(device):
+        mm = torch.empty(2, dtype=torch.int64, device=device)
+        rc = lib.agc_label_minmax(g.ptr, _abi.dtype_code(g.dtype), n, mm.data_ptr(), _stream_ptr(device))
+        if rc:
+            raise RuntimeError(_abi.last_error())
+        lo, hi = (int(v) for v in mm.cpu())
+        if lo < 0:
+            raise IndexError("negative labels in relabel_groups_unique")
+        keep = torch.zeros(hi + 1, dtype=torch.uint8, device=device)
+        status = torch.zeros(8, dtype=torch.int32, device=device)
+        rc = lib.agc_mark_present(g.ptr, _abi.dtype_code(g.dtype), n, hi + 1, keep.data_ptr(), status.data_ptr(), _stream_ptr(device))
+        if rc:
+            raise RuntimeError(_abi.last_error())
+    return _relabel(g, _Dev(keep, np.uint8), group_idx)
+
+
+def multi_arange(n):
+    """``hstack([arange(n_i) for n_i in n])`` (utils.py:572-594) on the device: running sums of ``n``, then every output
+    position finds its segment by bisection."""
+    torch = _require_cuda()
+    lib = _abi.load()
+    _check_int_1d(n, "n")
+    device = n.device if _is_tensor(n) and n.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    x = _as_device_ints(n, device)
+    m = x.t.numel()
+    if m == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    incl, total = _label_scan(_abi.LB_CUMSUM, x, want_total=True)
+    with torch.cuda.device(device):
+        out = _empty(total, np.int64, device)
+        rc = lib.agc_multi_arange(incl.ptr, m, total, out.ptr, _stream_ptr(device))
+        if rc:
+            raise RuntimeError(_abi.last_error())
+    return _finish_like(n, out)
+
+
+def is_duck_array(value):
+    """What the facade accepts as array input (utils.py:684-695): numpy arrays, anything that implements the numpy array
+    protocols, and -- for this implementation -- torch tensors (they stay on their device)."""
+    if isinstance(value, np.ndarray) or _is_tensor(value):
+        return True
+    return (hasattr(value, "ndim") and hasattr(value, "shape") and hasattr(value, "dtype")
+            and hasattr(value, "__array_function__") and hasattr(value, "__array_ufunc__"))

@@ -90,6 +90,7 @@ __global__ void k_init_tables(Tables t, long long size, int op, int a_dtype, int
       case AGC_OP_VAR: t.t0i[g] = 0; t.t1[g] = 0; t.t2[g] = 0.0; break;
       case AGC_OP_MAX: case AGC_OP_ARGMAX: t.t0i[g] = AGC_EMPTY_MAX; t.t1[g] = AGC_NO_INDEX; t.b1[g] = 0; break;
       case AGC_OP_MIN: case AGC_OP_ARGMIN: t.t0i[g] = AGC_EMPTY_MIN; t.t1[g] = AGC_NO_INDEX; t.b1[g] = 0; break;
+      case AGC_OP_MINMAX: t.t0i[g] = AGC_EMPTY_MAX; ((long long*)t.t2)[g] = AGC_EMPTY_MIN; t.b1[g] = 0; break;   // max keys in T0, min keys in T2
       case AGC_OP_ANY: case AGC_OP_ANYNAN: t.b0[g] = 0; t.b1[g] = 0; break;
       case AGC_OP_ALL: case AGC_OP_ALLNAN: t.b0[g] = 1; t.b1[g] = 0; break;
       case AGC_OP_FIRST: t.t1[g] = AGC_NO_INDEX; break;
@@ -160,6 +161,13 @@ __device__ __forceinline__ void accumulate_one(const AccParams& p, long long g, 
       if (k < t.t0i[g]) red_min_s64_hint(t.t0i + g, k, pol);
       if (!FL && !t.b1[g]) t.b1[g] = 1;
       break; }
+    case AGC_OP_MINMAX: {                            // fused multi-statistic pass: both extremes from one read of (labels, a)
+      const long long kmax = nan ? AGC_EMPTY_MIN : key_of(v), kmin = nan ? AGC_EMPTY_MAX : key_of(v);
+      long long* tmin = (long long*)t.t2;
+      if (kmax > t.t0i[g]) red_max_s64_hint(t.t0i + g, kmax, pol);
+      if (kmin < tmin[g]) red_min_s64_hint(tmin + g, kmin, pol);
+      if (!FL && !t.b1[g]) t.b1[g] = 1;
+      break; }
     case AGC_OP_ANY: if (v != T(0) && !t.b0[g]) t.b0[g] = 1; if (!t.b1[g]) t.b1[g] = 1; break;       // NaN is truthy; test-then-set keeps hot bytes read-only
     case AGC_OP_ALL: if (v == T(0) && t.b0[g]) t.b0[g] = 0; if (!t.b1[g]) t.b1[g] = 1; break;
     case AGC_OP_ANYNAN: if (nan && !t.b0[g]) t.b0[g] = 1; if (!t.b1[g]) t.b1[g] = 1; break;
@@ -205,7 +213,7 @@ __global__ void k_finalize(const FinParams p) {
   for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < p.size; g += stride) {
     switch (p.op) {
       case AGC_OP_SUM: case AGC_OP_SUMSQ: case AGC_OP_PROD:
-        if (need_touched && !t.b1[g]) fin_store_fill(p, g);
+        if (need_touched && ((p.flags & AGC_F_TOUCHED_BY_COUNT) ? t.t1[g] == 0 : !t.b1[g])) fin_store_fill(p, g);
         else if (fl) store_from_f64(p.out, p.out_dtype, g, t.t0f[g]);
         else store_from_i64(p.out, p.out_dtype, g, t.t0i[g], a_u64);
         break;
@@ -226,7 +234,7 @@ __global__ void k_finalize(const FinParams p) {
         if (!fill_nan && d == 0.0) fin_store_fill(p, g); else store_from_f64(p.out, p.out_dtype, g, r);
         break; }
       case AGC_OP_MAX: case AGC_OP_MIN: {
-        long long k = t.t0i[g];
+        long long k = (p.flags & AGC_F_KEYS_IN_T2) ? ((const long long*)t.t2)[g] : t.t0i[g];
         const long long empty = p.op == AGC_OP_MAX ? AGC_EMPTY_MAX : AGC_EMPTY_MIN;
         const long long nankey = p.op == AGC_OP_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX;
         if (a_fl) {

@@ -526,6 +526,55 @@ __device__ __forceinline__ void warp_store_blocked8(void* dst_warp, int4* wbuf, 
   __syncwarp();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// single-pass chained scan: tile descriptors + warp-parallel decoupled look-back
+// ---------------------------------------------------------------------------------------------
+// One 16-byte descriptor per tile, written and read as ONE 128-bit access: {meta, value bits}, meta = status (0 not
+// there yet, 1 tile aggregate, 2 inclusive prefix) | 0x100 when the tile holds a segment head (its value then is the
+// running value of the tile's LAST segment and nothing before the tile matters).  Warp 0 of tile t looks at the 32
+// tiles before it at once (lane l -> tile t - 1 - l), waits until they have published anything, folds the values up
+// to the nearest "terminator" (a prefix, or an aggregate with a head) with a bounded shuffle tree, and moves on by 32
+// tiles only if the window held none.  Tiles run in blockIdx order (tile 0 publishes its prefix at once), so every
+// descriptor a warp waits for belongs to a CTA that is already running or done.
+__device__ __forceinline__ void desc_store(unsigned long long* d, unsigned long long meta, unsigned long long xbits) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(d), "l"(meta), "l"(xbits) : "memory");
+}
+__device__ __forceinline__ void desc_load(const unsigned long long* d, unsigned long long& meta, unsigned long long& xbits) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(meta), "=l"(xbits) : "l"(d) : "memory");
+}
+template <class A> __device__ __forceinline__ unsigned long long scan_bits(A x);
+template <> __device__ __forceinline__ unsigned long long scan_bits<long long>(long long x) { return (unsigned long long)x; }
+template <> __device__ __forceinline__ unsigned long long scan_bits<double>(double x) { return (unsigned long long)__double_as_longlong(x); }
+template <class A> __device__ __forceinline__ A scan_unbits(unsigned long long b);
+template <> __device__ __forceinline__ long long scan_unbits<long long>(unsigned long long b) { return (long long)b; }
+template <> __device__ __forceinline__ double scan_unbits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+// called by the 32 threads of warp 0; returns the carry into tile t (t > 0): the running value at the end of tile t - 1
+template <class A, int OP>
+__device__ __forceinline__ A chain_lookback(const unsigned long long* desc, int t, int lane) {
+  A acc = A(0); bool have = false;
+  int look = t - 1 - lane;
+  for (;;) {
+    unsigned long long m = 2, xb = 0;                          // lanes past tile 0 never matter (tile 0 is a terminator)
+    if (look >= 0) { do { desc_load(desc + 2 * (long long)look, m, xb); } while ((m & 3ull) == 0ull); }
+    const bool term = (m & 3ull) == 2ull || (m & 0x100ull) != 0ull;
+    const unsigned tb = __ballot_sync(0xffffffffu, term);
+    const int first = tb ? __ffs((int)tb) - 1 : 32;            // nearest terminator in the window
+    A x = scan_unbits<A>(xb);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                         // lane i ends with the fold of lanes [i, first], farthest first
+      const A y = __shfl_down_sync(0xffffffffu, x, o);
+      if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+    }
+    const A win = __shfl_sync(0xffffffffu, x, 0);
+    acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
+    if (tb) break;
+    look -= 32;
+  }
+  return acc;
+}
+
 // Direct variant for flat int32/int64 labels that are already non-decreasing: no keys, no positions, no sort.
 // PHASE 0 reads (label, value) once for the tile aggregates and, on the way, verifies sortedness and label
 // bounds; PHASE 1 re-reads them, applies the carry and writes out[i] -- 40 B/element instead of the 64+ of the
@@ -561,7 +610,11 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
                                                                 const unsigned char* carry_ok, const A* carry_x) {
   // PHASE 1: nothing to do when the labels are not sorted; PHASE 0: another tile already found an inversion.
   // (block-uniform decision: every thread takes the same branch around the barriers below)
-  if (__syncthreads_or(*(volatile const int*)p.unsorted)) return;
+  // PHASE 2 (single pass, chained): tile_x carries the tile descriptors; a tile that gives up still publishes one
+  if (__syncthreads_or(*(volatile const int*)p.unsorted)) {
+    if (PHASE == 2 && threadIdx.x == 0) desc_store((unsigned long long*)tile_x + 2 * (long long)blockIdx.x, 2ull | 0x100ull, 0ull);
+    return;
+  }
   const long long base = (long long)blockIdx.x * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
   A x[SG_ITEMS]; bool h[SG_ITEMS];
   long long g[SG_ITEMS];
@@ -591,7 +644,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
     const long long i = base + k;
     if (i < p.n) {
       h[k] = (i == 0) || g[k] != prev;
-      if (PHASE == 0) { uns |= i > 0 && g[k] < prev; bad |= g[k] < 0 || g[k] >= p.size; }
+      if (PHASE != 1) { uns |= i > 0 && g[k] < prev; bad |= g[k] < 0 || g[k] >= p.size; }
       prev = g[k];
       x[k] = vec ? scan_from_raw<A, OP>(p, raw[k], h[k]) : scan_input<A, OP>(p, (unsigned)i, h[k]);
       if (!any) { tf = h[k]; tx = x[k]; any = true; }
@@ -599,7 +652,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
       x[k] = tx;                               // thread-local inclusive scan
     } else { h[k] = true; x[k] = A(0); }
   }
-  if (PHASE == 0) {
+  if (PHASE != 1) {
     if (uns) *p.unsorted_w = 1;
     if (bad) p.status[AGC_ST_BADLABEL] = 1;
   }
@@ -610,8 +663,27 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
     if (threadIdx.x == 0) { tile_f[blockIdx.x] = agg_f; tile_x[blockIdx.x] = agg_x; }
     return;
   }
-  bool have_c = blockIdx.x > 0 && carry_ok[blockIdx.x];
-  A cx = have_c ? carry_x[blockIdx.x] : A(0);
+  bool have_c; A cx;
+  if (PHASE == 2) {
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x < 32) {
+      unsigned long long* desc = (unsigned long long*)tile_x;
+      const int t = blockIdx.x;
+      // the aggregate first (tile 0: it already is the inclusive prefix), then the look-back, then the prefix
+      if (lane == 0) desc_store(desc + 2 * (long long)t, (t == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+      A c = A(0);
+      if (t > 0) {
+        c = chain_lookback<A, OP>(desc, t, lane);
+        if (lane == 0) desc_store(desc + 2 * (long long)t, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
+      }
+      if (lane == 0) s_carry = scan_bits<A>(c);
+    }
+    __syncthreads();
+    have_c = blockIdx.x > 0; cx = scan_unbits<A>(s_carry);
+  } else {
+    have_c = blockIdx.x > 0 && carry_ok[blockIdx.x];
+    cx = have_c ? carry_x[blockIdx.x] : A(0);
+  }
   bool have = false; A pre = A(0);
   if (have_p) { pre = px; have = true; if (have_c && !pf) pre = ScanOp<A, OP>::apply(cx, px); }
   else if (have_c) { pre = cx; have = true; }
@@ -776,7 +848,7 @@ __global__ void k_pos_select(const unsigned* p0, const unsigned* p1, const int* 
 // ---------------------------------------------------------------------------------------------
 inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 struct ScanWs {
-  int64_t k32[2], v[2], k64[2], v2[2], slot, gath, hist, tsum, tile_f, tile_x, carry_f, carry_x, flag, total;
+  int64_t k32[2], v[2], k64[2], v2[2], slot, gath, hist, tsum, tile_f, tile_x, carry_f, carry_x, desc, flag, total;
 };
 inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   ScanWs w; int64_t o = 0;
@@ -789,6 +861,7 @@ inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   w.hist = take(256ll * nb * 4); w.tsum = take((xs_tiles(256ll * nb) + 1) * 4);
   const long long ntiles = (n + SG_TILE - 1) / SG_TILE + 1;
   w.tile_f = take(ntiles); w.tile_x = take(ntiles * 8); w.carry_f = take(ntiles); w.carry_x = take(ntiles * 8);
+  w.desc = take(ntiles * 16);
   w.flag = take(256);
   w.total = o;
   return w;
@@ -831,12 +904,23 @@ inline void run_seg_scan(const ScanParams& p, char* ws, const ScanWs& L, cudaStr
   AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 1><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, nullptr, cf, cx);
 }
 
+// AGC_SCAN_CHAIN=0 (or agc_tuning key 6 = 0) selects the three-kernel direct scan instead of the chained single pass
+static int g_scan_chain = -1;
+inline bool scan_chain_enabled() {
+  if (g_scan_chain < 0) { const char* e = getenv("AGC_SCAN_CHAIN"); g_scan_chain = (e && atoi(e) == 0) ? 0 : 1; }
+  return g_scan_chain != 0;
+}
 template <class A, int OP, class LT>
 inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st) {
   if (p.n == 0) return;
   const int ntiles = (int)((p.n + SG_TILE - 1) / SG_TILE);
   unsigned char* tf = (unsigned char*)(ws + L.tile_f); A* tx = (A*)(ws + L.tile_x);
   unsigned char* cf = (unsigned char*)(ws + L.carry_f); A* cx = (A*)(ws + L.carry_x);
+  if (scan_chain_enabled()) {          // one pass, 24 B/element: tile descriptors + warp-parallel look-back
+    cudaMemsetAsync(ws + L.desc, 0, (size_t)ntiles * 16, st);
+    AGC_COUNT_LAUNCH(1), k_seg_scan_direct<A, OP, LT, 2><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, (A*)(ws + L.desc), nullptr, nullptr);
+    return;
+  }
   AGC_COUNT_LAUNCH(1), k_seg_scan_direct<A, OP, LT, 0><<<ntiles, SG_THREADS, 0, st>>>(p, tf, tx, nullptr, nullptr);
   AGC_COUNT_LAUNCH(1), k_seg_scan_tiles<A, OP><<<1, 1024, 0, st>>>(tf, tx, ntiles, cf, cx, p.unsorted, 0);
   AGC_COUNT_LAUNCH(1), k_seg_scan_direct<A, OP, LT, 1><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, nullptr, cf, cx);

@@ -9,6 +9,7 @@
 #include "agc_fast.cuh"
 #include "agc_dispatch.cuh"
 #include "agc_scan.cuh"
+#include "agc_labels.cuh"
 
 namespace {
 
@@ -57,7 +58,7 @@ agc::Tables tables_at(void* ws, const Layout& L) {
   return t;
 }
 
-bool is_reduction(int op) { return op >= AGC_OP_SUM && op <= AGC_OP_ANYNAN; }
+bool is_reduction(int op) { return (op >= AGC_OP_SUM && op <= AGC_OP_ANYNAN) || op == AGC_OP_MINMAX; }
 bool is_two_pass(int op) { return op == AGC_OP_VAR || op == AGC_OP_ARGMAX || op == AGC_OP_ARGMIN; }
 
 int check_request(const agc_request_t* r) {
@@ -71,6 +72,7 @@ int check_request(const agc_request_t* r) {
   if (r->index.form != AGC_FORM_FLAT && (r->index.ndim < 1 || r->index.ndim > AGC_MAX_NDIM)) return fail(-5, "bad ndim");
   if (r->n > 0 && !r->index.labels) return fail(-6, "null labels");
   if (!r->status) return fail(-6, "null status");
+  if (r->op == AGC_OP_MINMAX && !(r->flags & AGC_F_ACC_ONLY)) return fail(-2, "AGC_OP_MINMAX only accumulates (AGC_F_ACC_ONLY); finalise with op MAX / MIN");
   if (!r->out && !(r->flags & AGC_F_ACC_ONLY) && (r->size > 0 || !is_reduction(r->op))) return fail(-6, "null out");
   return 0;
 }
@@ -136,6 +138,7 @@ int agc_partials(const agc_request_t* r, agc_partial_t* out, int max_out) {
     case AGC_OP_VAR: if (pass2) add(L.t2, AGC_DT_F64, 0); else { add(L.t0, AGC_DT_F64, 0); add(L.t1, AGC_DT_I64, 0); } break;
     case AGC_OP_MAX: add(L.t0, AGC_DT_I64, 1); add(L.b1, AGC_DT_U8, 1); break;
     case AGC_OP_MIN: add(L.t0, AGC_DT_I64, 2); add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_MINMAX: add(L.t0, AGC_DT_I64, 1); add(L.t2, AGC_DT_I64, 2); add(L.b1, AGC_DT_U8, 1); break;
     case AGC_OP_ARGMAX: if (pass2) add(L.t1, AGC_DT_I64, 2); else add(L.t0, AGC_DT_I64, 1); break;
     case AGC_OP_ARGMIN: if (pass2) add(L.t1, AGC_DT_I64, 2); else add(L.t0, AGC_DT_I64, 2); break;
     case AGC_OP_ANY: case AGC_OP_ANYNAN: add(L.b0, AGC_DT_U8, 1); add(L.b1, AGC_DT_U8, 1); break;
@@ -237,6 +240,7 @@ float agc_profile_last_ms(void) {
 int64_t agc_launch_count(void) { return agc::g_launches; }
 int agc_tuning(int key, int value) {
   agc::tuning_defaults();
+  if (key == 6) { if (value >= 0) agc::g_scan_chain = value ? 1 : 0; return agc::scan_chain_enabled() ? 1 : 0; }
   if (key < 0 || key >= agc::TUNE_COUNT) return -1;
   if (value >= 0) agc::g_tune[key] = value;
   return agc::g_tune[key];
@@ -260,6 +264,41 @@ int agc_unpack(const void* table, int32_t elem_bytes, int64_t size, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   AGC_COUNT_LAUNCH(1), agc::k_unpack<<<grid_for(n, 256, 16), 256, 0, st>>>(table, elem_bytes, size, labels, dtype, n, out, status);
   AGC_CUDA_OK("unpack");
+  return 0;
+}
+
+int64_t agc_label_scan_workspace_bytes(int64_t n) { return agc::label_scan_workspace_bytes(n < 0 ? 0 : n); }
+
+int agc_label_scan(int32_t mode, const void* x, int32_t x_dtype, int64_t n, void* out, int32_t out_dtype, int64_t* total,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+  if (mode < 0 || mode > agc::LB_CUMSUM) return fail(-2, "agc_label_scan: unknown mode");
+  if (x_dtype < 0 || x_dtype > AGC_DT_U64) return fail(-3, "agc_label_scan: x must have a bool / integer dtype");
+  if (n < 0) return fail(-4, "negative n");
+  if (n > 0 && (!x || !workspace || (mode != agc::LB_STEP_COUNT && !out))) return fail(-6, "agc_label_scan: null pointer");
+  if (workspace_bytes < agc::label_scan_workspace_bytes(n)) return fail(-8, "workspace too small");
+  if (mode == agc::LB_KEEP && (out_dtype < 0 || out_dtype > AGC_DT_U64)) return fail(-3, "relabel table needs an integer dtype");
+  agc::LabelScanParams p;
+  p.x = x; p.x_dtype = x_dtype; p.n = n; p.out = out; p.out_dtype = out_dtype; p.total = (long long*)total; p.desc = nullptr;
+  int rc = agc::run_label_scan(mode, p, workspace, (cudaStream_t)stream);
+  if (rc) return fail(rc, "agc_label_scan failed");
+  AGC_CUDA_OK("label_scan");
+  return 0;
+}
+
+int agc_mark_present(const void* labels, int32_t dtype, int64_t n, int64_t size, void* keep, int32_t* status, void* stream) {
+  if (dtype < 0 || dtype > AGC_DT_U64) return fail(-3, "labels must have an integer dtype");
+  if (n <= 0) return 0;
+  if (!labels || !keep || !status) return fail(-6, "agc_mark_present: null pointer");
+  AGC_COUNT_LAUNCH(1), agc::k_mark_present<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(labels, dtype, n, size, (unsigned char*)keep, status);
+  AGC_CUDA_OK("mark_present");
+  return 0;
+}
+
+int agc_multi_arange(const int64_t* incl, int64_t m, int64_t total, int64_t* out, void* stream) {
+  if (total <= 0 || m <= 0) return 0;
+  if (!incl || !out) return fail(-6, "agc_multi_arange: null pointer");
+  AGC_COUNT_LAUNCH(1), agc::k_multi_arange<<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>((const long long*)incl, m, total, (long long*)out);
+  AGC_CUDA_OK("multi_arange");
   return 0;
 }
 

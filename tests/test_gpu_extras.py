@@ -1,0 +1,200 @@
+"""GPU parity of the callers either side of the hot path: unpack / uaggregate, fused multi-statistic
+aggregation, device CSR grouping, label utilities, duck arrays.  Checked against the reference's stored answers
+(tests/golden/utils.npz) and against the oracle on seeded inputs; integer / index work is bit-exact."""
+import numpy as np
+import pytest
+
+import utils_golden
+from numpy_groupies_b200 import aggregate, aggregate_cuda as ac
+from oracle import aggregate_oracle as oracle
+from oracle import utils_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = utils_golden.cases()
+
+
+@pytest.mark.parametrize("cid,kind,d", CASES, ids=[f"{c}_{k}" for c, k, _ in CASES])
+def test_utils_golden_case(cid, kind, d):
+    got = np.asarray(utils_golden.run(kind, d, ac, aggregate))
+    ref = d["out"]
+    assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
+    assert got.shape == ref.shape
+    if kind.startswith("uaggregate_") and ref.dtype.kind == "f":
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+    else:
+        np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("n", [1, 31, 2048, 2049, 1 << 20, (1 << 22) + 77])
+def test_step_indices_multi_tile(n):
+    rng = np.random.default_rng(n)
+    g = np.repeat(rng.integers(0, 1000, n // 3 + 1), rng.integers(1, 6, n // 3 + 1))[:n]
+    np.testing.assert_array_equal(ac.step_indices(g), utils_oracle.step_indices(g))
+    assert ac.step_count(g) == utils_oracle.step_count(g)
+
+
+def test_step_indices_empty_and_device_tensor():
+    import torch
+    assert ac.step_count(np.array([], dtype=np.int64)) == 0
+    np.testing.assert_array_equal(ac.step_indices(np.array([], dtype=np.int64)), [0])
+    g = torch.tensor([4, 4, 1, 1, 1, 9], device="cuda")
+    res = ac.step_indices(g)
+    assert res.is_cuda
+    np.testing.assert_array_equal(res.cpu().numpy(), [0, 2, 5, 6])
+
+
+@pytest.mark.parametrize("dtype", [bool, np.int8, np.int32, np.int64, np.uint16])
+def test_label_contiguous_large(dtype):
+    rng = np.random.default_rng(3)
+    n = (1 << 21) + 5
+    x = np.repeat(rng.integers(0, 3, n // 4 + 1), rng.integers(1, 8, n // 4 + 1))[:n]
+    x = (x != 0) if dtype is bool else x.astype(dtype)
+    np.testing.assert_array_equal(ac.label_contiguous_1d(x), utils_oracle.label_contiguous_1d(x))
+
+
+def test_label_contiguous_rejects_2d():
+    with pytest.raises(ValueError):
+        ac.label_contiguous_1d(np.zeros((3, 3), dtype=bool))
+
+
+def test_relabel_and_multi_arange_large():
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 300000, 1 << 21) * 2
+    got = ac.relabel_groups_unique(g)
+    ref = utils_oracle.relabel_groups_unique(g)
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
+    keep = rng.random(int(g.max()) + 1) < 0.3
+    np.testing.assert_array_equal(ac.relabel_groups_masked(g, keep), utils_oracle.relabel_groups_masked(g, keep))
+    n = rng.integers(0, 9, 300000)
+    np.testing.assert_array_equal(ac.multi_arange(n), utils_oracle.multi_arange(n))
+    with pytest.raises(ValueError):
+        ac.multi_arange(np.zeros((2, 2), dtype=int))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int16, np.uint8, bool])
+def test_unpack_dtypes_and_shapes(dtype):
+    rng = np.random.default_rng(11)
+    table = (rng.random(5000) * 100).astype(dtype)
+    g = rng.integers(0, 5000, (37, 1001))
+    got = ac.unpack(g, table)
+    assert got.dtype == table.dtype and got.shape == g.shape
+    np.testing.assert_array_equal(got, table[g])
+
+
+def test_unpack_out_of_range_raises_and_device_roundtrip():
+    import torch
+    with pytest.raises(IndexError):
+        ac.unpack(np.array([0, 5]), np.arange(5.0))
+    g = torch.randint(0, 100, (1 << 20,), device="cuda")
+    t = torch.rand(100, device="cuda", dtype=torch.float64)
+    res = ac.unpack(g, t)
+    assert res.is_cuda and torch.equal(res, t[g])
+    full = ac.uaggregate(g, t[g], func="max", size=100)
+    assert full.is_cuda and torch.equal(full, t[g])           # every element equals its group's max here
+
+
+@pytest.mark.parametrize("adtype", [np.float32, np.float64])
+@pytest.mark.parametrize("groups", [100, 5000, 200000])
+@pytest.mark.parametrize("fill", [0, -1.5, np.nan])
+def test_aggregate_multi_matches_single_calls(adtype, groups, fill):
+    rng = np.random.default_rng(groups)
+    n = 1 << 20
+    g = rng.integers(0, groups, n)
+    g[g == 7] = 8                                             # an empty group
+    a = rng.standard_normal(n).astype(adtype)
+    a[rng.random(n) < 0.05] = np.nan
+    funcs = ["sum", "mean", "len", "var", "std", "min", "max", "nansum", "nanmean", "nanvar", "nanlen", "nanmin", "nanmax", "first"]
+    res = ac.aggregate_multi(g, a, funcs, size=groups, fill_value=fill, ddof=1)
+    assert list(res) == funcs
+    for f in funcs:
+        kw = {"ddof": 1} if f.replace("nan", "") in ("var", "std") else {}
+        try:
+            one = aggregate(g, a, f, size=groups, fill_value=fill, **kw)
+        except ValueError:                                    # e.g. len with fill nan: the fused call raised too or fell back
+            continue
+        assert res[f].dtype == one.dtype and res[f].shape == one.shape, f
+        if f in ("len", "nanlen", "min", "max", "nanmin", "nanmax", "first"):
+            np.testing.assert_array_equal(res[f], one, err_msg=f)
+        else:
+            np.testing.assert_allclose(res[f], one, rtol=1e-5 if adtype == np.float32 else 1e-12, atol=1e-30, err_msg=f)
+
+
+def test_aggregate_multi_against_oracle_and_launch_savings():
+    from numpy_groupies_b200 import _abi
+    rng = np.random.default_rng(1)
+    n, groups = 1 << 21, 1000
+    g = rng.integers(0, groups, n)
+    a = rng.random(n)
+    lib = _abi.load()
+    before = lib.agc_launch_count()
+    res = ac.aggregate_multi(g, a, ["min", "max", "mean", "sum", "len"], size=groups)
+    fused = lib.agc_launch_count() - before
+    before = lib.agc_launch_count()
+    for f in ("min", "max", "mean", "sum", "len"):
+        aggregate(g, a, f, size=groups)
+    separate = lib.agc_launch_count() - before
+    assert fused < separate
+    for f in ("min", "max", "len"):
+        np.testing.assert_array_equal(res[f], oracle.aggregate(g, a, func=f, size=groups))
+    for f in ("mean", "sum"):
+        np.testing.assert_allclose(res[f], oracle.aggregate(g, a, func=f, size=groups), rtol=1e-12)
+
+
+def test_aggregate_multi_integer_values_and_forms():
+    rng = np.random.default_rng(2)
+    g = rng.integers(0, 50, (2, 40000))
+    a = rng.integers(-1000, 1000, 40000)
+    res = ac.aggregate_multi(g, a, ["min", "max", "sum", "mean"], size=(50, 50))
+    for f, r in res.items():
+        ref = oracle.aggregate(g, a, func=f, size=(50, 50))
+        assert r.dtype == ref.dtype and r.shape == ref.shape
+        np.testing.assert_allclose(r, ref, rtol=1e-12)
+    a3 = rng.random((64, 3000)).astype(np.float32)
+    g3 = rng.integers(0, 40, 3000)
+    res = ac.aggregate_multi(g3, a3, ["min", "max", "mean", "std"], size=40, axis=1)
+    for f, r in res.items():
+        ref = oracle.aggregate(g3, a3, func=f, size=40, axis=1)
+        assert r.shape == ref.shape
+        np.testing.assert_allclose(r, ref, rtol=1e-5)
+
+
+def test_group_csr_is_the_stable_grouping():
+    import torch
+    rng = np.random.default_rng(9)
+    n, groups = 300000, 777
+    g = rng.integers(0, groups, n)
+    a = rng.random(n)
+    order, offsets, values = ac.group_csr(torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda(), size=groups)
+    assert order.is_cuda and offsets.is_cuda and values.is_cuda
+    ref_order = np.argsort(g, kind="stable")
+    np.testing.assert_array_equal(order.cpu().numpy(), ref_order)
+    np.testing.assert_array_equal(offsets.cpu().numpy(), np.concatenate(([0], np.cumsum(np.bincount(g, minlength=groups)))))
+    np.testing.assert_array_equal(values.cpu().numpy(), a[ref_order])
+    # a device-side per-group function on top of it: segment maxima via the CSR offsets == aggregate(max)
+    vals, offs = values.cpu().numpy(), offsets.cpu().numpy()
+    seg_max = np.array([vals[offs[i]:offs[i + 1]].max() if offs[i + 1] > offs[i] else 0.0 for i in range(groups)])
+    np.testing.assert_array_equal(seg_max, aggregate(g, a, "max", size=groups))
+
+
+def test_duck_arrays():
+    import torch
+
+    class Duck:                                               # minimal array-protocol object (utils.py:684-695)
+        def __init__(self, arr):
+            self._a = arr
+            self.ndim, self.shape, self.dtype = arr.ndim, arr.shape, arr.dtype
+
+        def __array__(self, dtype=None, copy=None):
+            return self._a
+
+        def __array_function__(self, *args, **kw):
+            return NotImplemented
+
+        def __array_ufunc__(self, *args, **kw):
+            return NotImplemented
+
+    g, a = np.array([0, 1, 1, 3]), np.array([1.0, 2.0, 3.0, 4.0])
+    assert ac.is_duck_array(Duck(a)) and ac.is_duck_array(a) and ac.is_duck_array(torch.zeros(2)) and not ac.is_duck_array([1, 2])
+    np.testing.assert_array_equal(aggregate(Duck(g), Duck(a)), [1.0, 5.0, 0.0, 4.0])

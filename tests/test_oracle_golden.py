@@ -22,3 +22,17 @@ def test_oracle_matches_reference(case):
         res = oracle.aggregate(gidx, a, func=func, **kwargs)
     # same primitives in the same order => bit-identical floats too
     check_result(G, case, res, exact_float=True)
+
+
+def test_utils_oracle_matches_reference():
+    """oracle/utils_oracle.py == the reference's label utilities / unpack on every stored case, bit for bit."""
+    import utils_golden
+    from oracle import aggregate_oracle, utils_oracle
+    n = 0
+    for cid, kind, d in utils_golden.cases():
+        got = utils_golden.run(kind, d, utils_oracle, aggregate_oracle.aggregate)
+        ref = d["out"]
+        assert np.asarray(got).dtype == ref.dtype, (cid, kind, np.asarray(got).dtype, ref.dtype)
+        np.testing.assert_array_equal(got, ref, err_msg=f"case {cid} {kind}")
+        n += 1
+    assert n >= 30
