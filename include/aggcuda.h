@@ -172,6 +172,26 @@ int         agc_mark_present(const void* labels, int32_t dtype, int64_t n, int64
 /* multi_arange (utils.py:572-594): incl = inclusive running sums of n (int64[m]), out = int64[total] */
 int         agc_multi_arange(const int64_t* incl, int64_t m, int64_t total, int64_t* out, void* stream);
 
+/* ---- multi-GPU helpers (numpy_groupies_b200/distributed.py) -------------------------------------------------
+ * agc_pack_tables: gather up to 8 tables of different dtypes (float64 / int64 / int32 / uint8) into ONE homogeneous
+ * buffer (`carrier_dtype` float64 or int64) so that a merge is a single all-reduce, or (unpack != 0) scatter the reduced
+ * buffer back.  xform per table: 0 value as is, 1 negated (a MAX table riding in a MIN reduction and vice versa),
+ * 2 flag (a 0/1 table riding in a SUM: any non-zero reads back as 1), 3 negated flag. */
+typedef struct agc_pack_seg { void* table; int64_t count; int32_t dtype; int32_t xform; } agc_pack_seg_t;
+int         agc_pack_tables(const agc_pack_seg_t* segs, int32_t nseg, void* packed, int32_t carrier_dtype, int32_t unpack, void* stream);
+/* cross-GPU carry exchange of the N->N functions: gathered = [world][size] per-group totals of every rank in the T0
+ * representation of the matching reduction (float64 / int64 sums and products, int64 order-preserving keys for max / min;
+ * reduce: 0 sum, 1 max, 2 min, 3 prod).  carry[g] = fold of the ranks before `rank`, in rank order. */
+int         agc_rank_fold(const void* gathered, int32_t rank, int64_t size, int32_t dtype, int32_t reduce, void* carry, void* stream);
+/* out[i] = carry[labels[i]] (op) out[i] for op in AGC_OP_CUMSUM / CUMPROD / CUMMAX / CUMMIN (out = this rank's local scan) */
+int         agc_apply_carry(int32_t op, const void* labels, int32_t label_dtype, int64_t n, int64_t size, void* out, int32_t out_dtype,
+                            int32_t a_dtype, const void* carry, int32_t carry_dtype, int32_t* status, void* stream);
+
+/* first / last over shards (after the index tables were merged and req was finalised with AGC_F_FIN_ONLY): pack writes
+ * carrier[g] = bits of out[g] where THIS shard holds the group's winning element, else 0 (one int64 SUM all-reduce hands
+ * every rank the owner's bits); unpack stores them into out[g] for every non-empty group. */
+int         agc_owner_pack(const agc_request_t* req, int64_t* carrier, int32_t unpack, void* stream);
+
 /* measurement hooks (bench.py): when enabled, agc_aggregate brackets its dominant accumulate kernel with
  * CUDA events on the caller's stream; agc_profile_last_ms() waits for that kernel and returns its duration.
  * agc_launch_count() = number of libaggcuda kernels launched by this process so far. */
@@ -189,7 +209,10 @@ int64_t     agc_launch_count(void);
  *   key 5  a partial table keeps the key-3 size while at most this percentage of the groups stays uncovered; beyond
  *          that it grows to the full 226 KB (default 10)
  *   key 6  sorted-label scans: 1 single-pass chained scan with warp-parallel look-back (default), 0 the three-kernel
- *          reduce / scan-tiles / apply variant */
+ *          reduce / scan-tiles / apply variant
+ *   key 7  sums / means on tables larger than one SM: thread-block clusters of this many SMs (2 | 4) own the table together
+ *          and exchange records over DSMEM (k_team); 0 = partial table + global RED (the round-1 kernels).  Default 2
+ *   key 8  k_team runs while at most this percentage of the groups stays without a slot (default 60) */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus

@@ -45,10 +45,17 @@ class Partial(C.Structure):
     _fields_ = [("offset_bytes", C.c_int64), ("count", C.c_int64), ("dtype", C.c_int32), ("reduce", C.c_int32)]
 
 
+class PackSeg(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("count", C.c_int64), ("dtype", C.c_int32), ("xform", C.c_int32)]
+
+
+PK_COPY, PK_NEG, PK_FLAG, PK_NEGFLAG = 0, 1, 2, 3
+
 EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_partials", "agc_aggregate",
            "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order",
            "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count", "agc_tuning",
-           "agc_label_scan_workspace_bytes", "agc_label_scan", "agc_mark_present", "agc_multi_arange")
+           "agc_label_scan_workspace_bytes", "agc_label_scan", "agc_mark_present", "agc_multi_arange",
+           "agc_pack_tables", "agc_rank_fold", "agc_apply_carry", "agc_owner_pack")
 
 _lib = None
 
@@ -93,6 +100,15 @@ def load():
     lib.agc_mark_present.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.agc_multi_arange.restype = C.c_int
     lib.agc_multi_arange.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.agc_pack_tables.restype = C.c_int
+    lib.agc_pack_tables.argtypes = [C.POINTER(PackSeg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.agc_owner_pack.restype = C.c_int
+    lib.agc_owner_pack.argtypes = [C.POINTER(Request), C.c_void_p, C.c_int32, C.c_void_p]
+    lib.agc_rank_fold.restype = C.c_int
+    lib.agc_rank_fold.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.agc_apply_carry.restype = C.c_int
+    lib.agc_apply_carry.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.agc_profile_enable.restype = C.c_int
     lib.agc_profile_enable.argtypes = [C.c_int]
     lib.agc_profile_last_ms.restype = C.c_float

@@ -40,14 +40,15 @@ _LAST = {"regime": 0, "probe": (0, 0, 0)}
 def last_regime():
     """Which accumulate kernel the last checked call used (status[3] of the C ABI): 0 general global-table
     kernel, 10+mode k_fast (mode: 0 sum, 1 sum+count, 2 max, 3 min, 4 len, 5 one-word sum), 16 k_len16, 17 / 18
-    k_maxfilter max / min, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs, 60 k_accumulate_small."""
+    k_maxfilter max / min, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs, 60 k_accumulate_small, 70 / 71 k_team (sums /
+    sums + counts on a cluster of SMs)."""
     return _LAST["regime"]
 
 
-def tuning(large=-1, cache_ctas=-1, sum1=-1, smem1=-1, smem2=-1, uncov_pct=-1, scan_chain=-1):
+def tuning(large=-1, cache_ctas=-1, sum1=-1, smem1=-1, smem2=-1, uncov_pct=-1, scan_chain=-1, team=-1, team_maxu=-1):
     """Kernel-selection knobs of libaggcuda (agc_tuning, include/aggcuda.h): for tests and A/B measurements."""
     lib = _abi.load()
-    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1, smem1, smem2, uncov_pct, scan_chain)))
+    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1, smem1, smem2, uncov_pct, scan_chain, team, team_maxu)))
 
 
 def _t():
@@ -826,7 +827,7 @@ def _fused_family(group_idx, a, members, family, size, fill_value, order, axis, 
                 raise RuntimeError(f"agc_aggregate failed ({rc}): {_abi.last_error()}")
 
         # workspace: the reduction layout does not depend on the op
-        req.op, req.flags, req.out_dtype, req.out = _abi.OP["mean"], 0, _abi.dtype_code(np.dtype(np.float64)), 0
+        req.op, req.flags, req.out_dtype, req.out = _abi.OP["mean"], _abi.F_ACC_ONLY, _abi.dtype_code(np.dtype(np.float64)), 0
         ws_bytes = lib.agc_workspace_bytes(C.byref(req))
         if ws_bytes < 0:
             raise RuntimeError(_abi.last_error())

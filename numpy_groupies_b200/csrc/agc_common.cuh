@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/aggcuda.h"
 
 #define AGC_EMPTY_MAX  ((long long)0x8000000000000000ll)   // "no element yet" for max-keys
@@ -17,14 +18,29 @@
 namespace agc {
 
 // kernels launched by this library so far (bench.py reports it as `gpu_launches`)
-static long long g_launches = 0;
-#define AGC_COUNT_LAUNCH(n_) (::agc::g_launches += (n_))
+static std::atomic<long long> g_launches{0};
+#define AGC_COUNT_LAUNCH(n_) (::agc::g_launches.fetch_add((n_), std::memory_order_relaxed))
 
-// SM count of the current device (cached); grid cap for the tile-loop kernels
+// ---- per-DEVICE host state (a process may drive several GPUs, from several threads) ----------------------------------
+constexpr int AGC_MAX_DEVICES = 64;
+inline int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev < 0 || dev >= AGC_MAX_DEVICES) ? 0 : dev; }
+// SM count of the CURRENT device; grid cap for the tile-loop kernels
 inline int device_sms() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  return sms;
+  static std::atomic<int> sms[AGC_MAX_DEVICES];
+  const int dev = current_device();
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (!v) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (v <= 0) v = 148; sms[dev].store(v, std::memory_order_relaxed); }
+  return v;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device / context: `done` remembers the devices it was set on.
+// Returns false if the attribute cannot be set.
+template <class K>
+inline bool ensure_dyn_smem(K kern, int bytes, std::atomic<unsigned long long>& done) {
+  const int dev = current_device();
+  if (done.load(std::memory_order_acquire) >> dev & 1ull) return true;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+  done.fetch_or(1ull << dev, std::memory_order_release);
+  return true;
 }
 inline int tile_grid(long long ntiles, int ctas_per_sm) {
   const long long cap = (long long)device_sms() * ctas_per_sm;

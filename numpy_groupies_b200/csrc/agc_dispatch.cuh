@@ -21,6 +21,8 @@
 #include "agc_fast.cuh"
 #include "agc_form3.cuh"
 #include "agc_runs.cuh"
+#include "agc_team.cuh"
+#include <mutex>
 
 namespace agc {
 
@@ -100,10 +102,15 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
 //   key 4  AGC_SMEM2      the same for kernels that run two CTAs per SM (default 99200)
 //   key 5  AGC_UNCOV_PCT  a partial table keeps the 195 KB size while at most this percentage of the groups stays uncovered,
 //                         beyond that it grows to 226 KB (default 10; measured crossover 9-17 %, scripts/uncov_sweep.py)
-enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_UNCOV = 5, TUNE_COUNT = 6 };
-static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1, -1};
-inline void tuning_defaults() {
-  if (g_tune[0] >= 0) return;
+//   key 6  (agc_scan.cuh) sorted-label scans: chained single pass (1, default) or the three-kernel variant (0)
+//   key 7  AGC_TEAM       sums / means on tables larger than one SM: thread-block clusters of this many SMs own the table
+//                         together and exchange records over DSMEM (k_team, agc_team.cuh); 0 = partial table + global RED
+//                         as in round 1.  Default 2.
+//   key 8  AGC_TEAM_MAXU  k_team runs while at most this percentage of the groups stays without a slot (default 60)
+enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_UNCOV = 5, TUNE_SCAN_CHAIN = 6, TUNE_TEAM = 7,
+       TUNE_TEAM_MAXU = 8, TUNE_COUNT = 9 };
+static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+inline void tuning_defaults_once() {
   const char* e;
   e = getenv("AGC_LARGE");      g_tune[TUNE_LARGE] = e ? atoi(e) : 1;
   if (g_tune[TUNE_LARGE] != 0 && g_tune[TUNE_LARGE] != 3 && g_tune[TUNE_LARGE] != 4) g_tune[TUNE_LARGE] = 1;
@@ -112,6 +119,21 @@ inline void tuning_defaults() {
   e = getenv("AGC_SMEM1");      g_tune[TUNE_SMEM1] = e ? atoi(e) : 199552;
   e = getenv("AGC_SMEM2");      g_tune[TUNE_SMEM2] = e ? atoi(e) : 99200;
   e = getenv("AGC_UNCOV_PCT");  g_tune[TUNE_UNCOV] = e ? atoi(e) : 10;
+  g_tune[TUNE_SCAN_CHAIN] = 1;                                 // lives in agc_scan.cuh (agc_tuning forwards key 6)
+  e = getenv("AGC_TEAM");       g_tune[TUNE_TEAM] = e ? atoi(e) : 2;
+  if (g_tune[TUNE_TEAM] != 0 && g_tune[TUNE_TEAM] != 2 && g_tune[TUNE_TEAM] != 4) g_tune[TUNE_TEAM] = 2;
+  e = getenv("AGC_TEAM_MAXU");  g_tune[TUNE_TEAM_MAXU] = e ? atoi(e) : 60;
+}
+inline void tuning_defaults() { static std::once_flag once; std::call_once(once, tuning_defaults_once); }
+
+// k_team launcher over its template grid; returns the number of clusters (> 0), or < 0 if the cluster launch is not possible
+template <class LT>
+inline int launch_team_lt(int C, int mode, bool nanskip, const TeamParams& tp, size_t smem, cudaStream_t st) {
+#define AGC_TEAM_ONE(C_, M_)                                                                                          \
+  if (C == C_ && mode == M_) return nanskip ? launch_team<C_, LT, M_, true>(tp, smem, st) : launch_team<C_, LT, M_, false>(tp, smem, st);
+  AGC_TEAM_ONE(2, TM_SUM) AGC_TEAM_ONE(2, TM_SUMCNT) AGC_TEAM_ONE(4, TM_SUM) AGC_TEAM_ONE(4, TM_SUMCNT)
+#undef AGC_TEAM_ONE
+  return -33;
 }
 inline size_t smem_cap1() { int v = g_tune[TUNE_SMEM1]; return (size_t)(v < 16384 ? 16384 : (v > 227 * 1024 - 1024 ? 227 * 1024 - 1024 : v)); }
 inline size_t smem_cap2() { int v = g_tune[TUNE_SMEM2]; return (size_t)(v < 8192 ? 8192 : (v > 110 * 1024 ? 110 * 1024 : v)); }
@@ -352,7 +374,30 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
         else     rc = nanskip ? launch_len16<int, true>(p, st, sms) : launch_len16<int, false>(p, st, sms);
       } else run_fast(FM_LEN, 1, nanskip, no_limit);             // u32 counts: < 2^32 elements per CTA
     };
-    if (sum1) run_fast(FM_SUM1, 1, true, no_limit);
+    // ---- k_team: a cluster of SMs owns the table together (no scattered RED for the groups it covers) -------------
+    bool team_done = false;
+    const int team_c = g_tune[TUNE_TEAM];
+    if (team_c && need_a && !p.square && (mode == FM_SUM || mode == FM_SUMCNT) && g_tune[TUNE_SUM1] != 0) {
+      const int tmode = mode == FM_SUM ? TM_SUM : TM_SUMCNT;
+      const int tcap = team_default_cap(team_c);
+      const long long fixed = (long long)team_smem_bytes(team_c, tmode, 0, tcap) + 16;
+      const long long slots = ((long long)cap1 - fixed) / (tmode == TM_SUM ? 4 : 6);
+      long long cov = r->size / team_c;                         // cov * C <= size (the kernel relies on it)
+      if (cov > slots) cov = slots;
+      const double uncovered = 1.0 - (double)(cov * team_c) / (double)r->size;
+      if (cov >= 1024 && uncovered * 100.0 <= (double)g_tune[TUNE_TEAM_MAXU]) {
+        TeamParams tp;
+        tp.labels = r->index.labels; tp.a = (const float*)r->a; tp.n = r->n; tp.size = r->size; tp.t = t; tp.status = r->status;
+        tp.flags = r->flags; tp.want_cnt = p.want_cnt; tp.want_b1 = p.want_b1; tp.cov = (int)cov; tp.cap = tcap;
+        tp.choose = probe ? choose : nullptr; tp.want = 0; tp.dbg = 0;
+        const size_t tsmem = team_smem_bytes(team_c, tmode, (int)cov, tcap);
+        const int trc = i64 ? launch_team_lt<long long>(team_c, tmode, nanskip, tp, tsmem, st) : launch_team_lt<int>(team_c, tmode, nanskip, tp, tsmem, st);
+        if (trc > 0) team_done = true;
+        else cudaGetLastError();                                // clusters not available: the round-1 kernels below take over
+      }
+    }
+    if (team_done) {}
+    else if (sum1) run_fast(FM_SUM1, 1, true, no_limit);
     else if (split) {
       run_fast(FM_SUM1, 1, true, no_limit);
       if (rc >= 0) run_len();

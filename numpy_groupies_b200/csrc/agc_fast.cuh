@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   auto update = [&](long long g, float x) {
     if (g < 0 || g >= p.size) { bad = true; return; }
     if (IS_SUM && xmeans) {
+      // nan-forms drop ORIGINAL NaNs only: a NaN deviation of a non-NaN element (+-inf in the group) must propagate, as in
+      // the reference's (a - mean)**2 (aggregate_numpy.py:184-186)
+      if (nanskip && x != x) return;
       if (mpair) { const float2 hl = mpair[g]; const float d = (x - hl.x) - hl.y; x = d * d; }
       else { const double d = (double)x - __ldg(xmeans + g); x = (float)(d * d); }
     }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       else k = key32_of(x);
       if (MODE == FM_MAX) atomicMax((int*)w0 + gi, k); else atomicMin((int*)w0 + gi, k);
     } else {
-      if (nanskip && x != x) return;
+      if (nanskip && !xmeans && x != x) return;
       if (p.square) x = x * x;
       unsigned ab = __float_as_uint(x) & 0x7fffffffu;
       if (ab - lo_bits < span_bits) {
@@ -406,11 +409,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_len16(const FastParams p) {
 template <class LT, bool LOAD_A>
 inline int launch_len16(const FastParams& p, cudaStream_t st, int sms) {
   auto kern = k_len16<LT, LOAD_A>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dyn_smem(kern, 227 * 1024 - 64, attr_done)) return -30;
   const size_t smem = (size_t)((p.cov + 1) / 2) * 4;
   AGC_COUNT_LAUNCH(1), kern<<<sms, FAST_THREADS, smem, st>>>(p);
   return 1;
@@ -516,11 +516,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) k_maxfilter(const FastParams 
 template <bool ISMAX, class LT, bool TIE>
 inline int launch_maxfilter(const FastParams& p, cudaStream_t st, int sms) {
   auto kern = k_maxfilter<ISMAX, LT, TIE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dyn_smem(kern, 227 * 1024 - 64, attr_done)) return -30;
   const size_t smem = (size_t)((p.cov + 1) / 2) * 4;
   AGC_COUNT_LAUNCH(1), kern<<<sms, FAST_THREADS, smem, st>>>(p);
   return 1;
@@ -677,11 +674,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
 template <int MODE, class LT, bool LOAD_A>
 inline int launch_cache(const FastParams& p, int ctas_per_sm, size_t smem, cudaStream_t st, int sms) {
   auto kern = k_cache<MODE, LT, LOAD_A>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dyn_smem(kern, 227 * 1024 - 64, attr_done)) return -30;
   AGC_COUNT_LAUNCH(1), kern<<<sms * ctas_per_sm, FAST_THREADS, smem, st>>>(p);
   return 1;
 }
@@ -689,11 +683,8 @@ inline int launch_cache(const FastParams& p, int ctas_per_sm, size_t smem, cudaS
 template <int MODE, class LT, bool LOAD_A, int U, bool PARTIAL, bool X>
 inline int launch_fast_x(const FastParams& p, int grid, size_t smem, cudaStream_t st) {
   auto kern = k_fast<MODE, LT, LOAD_A, U, PARTIAL, X>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dyn_smem(kern, 227 * 1024 - 64, attr_done)) return -30;
   AGC_COUNT_LAUNCH(1), kern<<<grid, FAST_THREADS, smem, st>>>(p);
   return 1;
 }

@@ -156,11 +156,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
 template <int MODE, class LT, int RB>
 inline int launch_form3_rb(const Form3Params& p, size_t smem, cudaStream_t st, int sms) {
   auto kern = k_form3<MODE, LT, RB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return -30;
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dyn_smem(kern, 110 * 1024, attr_done)) return -30;
   int grid = sms * 2;
   if (grid > p.n_items) grid = p.n_items;
   AGC_COUNT_LAUNCH(1), kern<<<grid, FAST_THREADS, smem, st>>>(p);

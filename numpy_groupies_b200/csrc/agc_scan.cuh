@@ -243,8 +243,8 @@ template <class K>
 inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int hi_bit, const int* run_flag, cudaStream_t st) {
   if (n == 0) return src;
   const int nb = rs_blocks_k<K>(n);
-  static bool attr_done = false;
-  if (!attr_done) { cudaFuncSetAttribute(k_radix_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<K>()); attr_done = true; }
+  static std::atomic<unsigned long long> attr_done{0};
+  ensure_dyn_smem(k_radix_scatter<K>, (int)rs_scatter_smem<K>(), attr_done);
   for (int shift = lo_bit; shift < hi_bit; shift += 8) {
     AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<tile_grid(nb, 4), RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, run_flag);
     exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st, run_flag);

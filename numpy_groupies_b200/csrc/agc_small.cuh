@@ -145,8 +145,11 @@ __global__ void __launch_bounds__(1024) k_accumulate_small(const AccParams p, in
 template <class T>
 inline void launch_accumulate_small(const AccParams& p, cudaStream_t st, int sms) {
   if ((size_t)p.size * 12 > SMALL_SMEM) {                 // one big table per SM, two CTAs of 512 threads cannot both hold it
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_accumulate_small<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_BIG); attr_done = true; }
+    static std::atomic<unsigned long long> attr_done{0};
+    if (!ensure_dyn_smem(k_accumulate_small<T>, (int)SMALL_SMEM_BIG, attr_done)) {       // cannot take the big table: general kernel
+      AGC_COUNT_LAUNCH(1), k_accumulate<T><<<tile_grid((p.n + 255) / 256, 16), 256, 0, st>>>(p);
+      return;
+    }
     long long blocks = (p.n + 1024 * 8 - 1) / (1024 * 8);
     if (blocks > sms) blocks = sms;
     AGC_COUNT_LAUNCH(1), k_accumulate_small<T><<<(int)blocks, 1024, (size_t)p.size * 12, st>>>(p, 0);

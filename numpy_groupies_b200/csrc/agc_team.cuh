@@ -31,16 +31,18 @@ struct TeamParams {
   Tables t;
   int* status;
   int flags;            // AGC_F_NANSKIP
-  int square;           // sumofsquares
   int want_cnt;         // TM_SUMCNT: merge counts into T1
   int want_b1;          // TM_SUMCNT: write touched flags
   int cov;              // table slots per CTA (group g -> CTA g % C, slot g / C; slots >= cov go to the global tables)
   int cap;              // 8-byte record slots per (peer, buffer, warp), slot 0 is the header {count}
   const int* choose;    // device word written by k_skew_probe; run iff *choose == want (NULL: always)
   int want;
+  int dbg;              // measurements only (ubench/team_probe): 1 every element is treated as mine (no exchange), 2 records are received but not applied
 };
 
 namespace dsm {
+// a value the compiler must keep in a register instead of re-deriving it at every use (the hot loop is instruction bound)
+__device__ __forceinline__ unsigned keep(unsigned x) { unsigned y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned mapa(unsigned saddr, unsigned rank) {
@@ -84,9 +86,10 @@ __device__ __forceinline__ void remote_arrive_release(unsigned rbar) {
 }
 }  // namespace dsm
 
-// XPORT 0: st.async records + relaxed arrive.expect_tx (no fence anywhere in the loop)
-// XPORT 1: plain st.shared::cluster records + release arrive (a fence per warp and phase) -- the fallback transport
-template <int C, class LT, int MODE, int XPORT>
+// Instruction budget: the kernel issues ~1.7 warp instructions per element (C = 2), so everything that is not on the
+// common path -- labels outside [0, cov * C), values outside the fixed-point window, NaN handling, a full buffer --
+// sits behind ONE rarely taken branch per element (`slow`).
+template <int C, class LT, int MODE, bool NANSKIP>
 __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
   if (p.choose && *p.choose != p.want) return;              // same decision in every CTA of the cluster
   extern __shared__ __align__(16) unsigned sw[];
@@ -97,7 +100,6 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
   constexpr bool HAS_CNT = MODE == TM_SUMCNT;
   static_assert(C == 2 || C == 4 || C == 8, "cluster size");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned me = dsm::ctarank();
   const int cov = p.cov, cap = p.cap;
 
@@ -118,9 +120,7 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
   const long long grid_vecs = (long long)gridDim.x * TEAM_THREADS;
   const long long nphase = (nvec + grid_vecs - 1) / grid_vecs;                     // the same for every warp of the grid
   long long v = (long long)blockIdx.x * TEAM_THREADS + threadIdx.x;
-  const bool nanskip = p.flags & AGC_F_NANSKIP;
-  const bool square = p.square != 0;
-  bool bad = false;
+  int bad = 0;
 
   // ---- one reference exponent per cluster (records carry fixed-point integers) ----------------------------------
   {
@@ -129,18 +129,14 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
       const int4 av = ldg_stream16((const int4*)p.a + v);
       const unsigned b[4] = {(unsigned)av.x & 0x7fffffffu, (unsigned)av.y & 0x7fffffffu, (unsigned)av.z & 0x7fffffffu, (unsigned)av.w & 0x7fffffffu};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        unsigned bb = b[k];
-        if (square) { const float f = __uint_as_float(bb); bb = __float_as_uint(f * f); }
-        if (bb < 0x7f800000u && bb > m) m = bb;
-      }
+      for (int k = 0; k < 4; ++k) if (b[k] < 0x7f800000u && b[k] > m) m = b[k];
     }
     m = __reduce_max_sync(0xffffffffu, m);
     if (lane == 0 && m) atomicMax(&s_maxbits, m);
     __syncthreads();
     if (threadIdx.x < C) dsm::st_remote_u32(dsm::mapa(dsm::smem_u32(&s_peer_max[me]), threadIdx.x), s_maxbits);
   }
-  dsm::cluster_sync();                // mbarrier inits and the exponent words are visible cluster-wide behind this
+  dsm::cluster_sync();                // the exponent words are visible cluster-wide behind this
   unsigned lo_bits = 0, span_bits = 0; float scale_f = 1.f; double inv_scale = 1.0;
   {
     unsigned mb = 0;
@@ -157,36 +153,49 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
     else scale_f = __int_as_float((se + 127) << 23);
     inv_scale = __longlong_as_double((long long)(1023 - se) << 52);
   }
-  const double hi_unit = inv_scale * 4294967296.0;
-  const unsigned long long pol = l2_evict_last_policy();
-  const unsigned cnt_sbase = dsm::smem_u32(cnt16);
+  const unsigned cnt_sbase = dsm::keep(dsm::smem_u32(cnt16));
+  const unsigned table_s = dsm::keep(dsm::smem_u32(table));
+  const unsigned cov_c = (unsigned)cov << LOGC;               // labels below this have a slot somewhere in the cluster (host: cov * C <= size)
+  const unsigned lt_mask = dsm::keep((1u << lane) - 1u);
+  const unsigned capm = (unsigned)cap;
 
   // ---- per-peer addresses: peer j = CTA (me + j + 1) % C receives into ITS region j; I receive region j from CTA (me - j - 1) % C,
   //      which is peer P - 1 - j.  The shared::cluster window of a CTA is linear: remote address = peer base + local offset.
-  unsigned rbase[P];
-  const unsigned sw_s = dsm::smem_u32(sw);
-#pragma unroll
-  for (int j = 0; j < P; ++j) rbase[j] = dsm::mapa(sw_s, (me + j + 1) & (C - 1)) - sw_s;
   constexpr unsigned BAR_B = TEAM_WARPS * 8;                   // bytes from a buffer-0 barrier to its buffer-1 twin
   const unsigned buf_stride = (unsigned)(TEAM_WARPS * cap * 8);  // bytes from buffer 0 to buffer 1 of a region
+  const unsigned sw_s = dsm::smem_u32(sw);
   const unsigned in0 = dsm::smem_u32(inbox) + (unsigned)warp * cap * 8u;      // my region 0, buffer 0 (region j: + j * 2 * buf_stride)
-  const unsigned full0 = dsm::smem_u32(bars) + (unsigned)warp * 8u;           // full[0][0][warp] (region j: + j * 2 * BAR_B)
+  const unsigned full0 = dsm::keep(dsm::smem_u32(bars) + (unsigned)warp * 8u);  // full[0][0][warp] (region j: + j * 2 * BAR_B)
   const unsigned empty0 = full0 + P * 2 * BAR_B;                             // empty[0][0][warp]
+  unsigned dst0[P], dbar0[P], rempty0[P];                      // buffer-0 addresses at the peers: records, "full" barrier; "empty" barrier of the sender of region j
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const unsigned rb = dsm::mapa(sw_s, (me + j + 1) & (C - 1)) - sw_s;
+    const unsigned rs = dsm::mapa(sw_s, (me - j - 1) & (C - 1)) - sw_s;
+    dst0[j] = dsm::keep(rb + in0 + (j * 2) * buf_stride);
+    dbar0[j] = dsm::keep(rb + full0 + (j * 2) * BAR_B);
+    rempty0[j] = dsm::keep(rs + empty0 + (j * 2) * BAR_B);
+  }
 
   // ---- element sinks ---------------------------------------------------------------------------------------
+  // (rarely used constants -- the L2 policy, the value of a carry -- are re-derived where they are needed: registers are short)
+  const double hi_unit = inv_scale * 4294967296.0;            // what one carry out of a 32-bit word is worth
   auto repair = [&](unsigned wi, int sh, long long g) {        // k_len16's read-check-repair: take 0x8000 out, forward it
     unsigned o = *(volatile unsigned*)(cnt16 + wi);
     while (((o >> sh) & 0xffffu) >= 0x8000u) {
       const unsigned seen = atomicCAS(cnt16 + wi, o, o - (0x8000u << sh));
-      if (seen == o) { red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 0x8000ull, pol); break; }
+      if (seen == o) { red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 0x8000ull, l2_evict_last_policy()); break; }
       o = seen;
     }
   };
-  auto apply = [&](unsigned li, int q) {                       // a record (or an own element) into MY table
+  // a record (or an own element) into MY table: one native ATOMS.ADD; a carry / borrow out of the 32-bit word (the add
+  // wrapped although q >= 0, or did not although q < 0) is forwarded at once as an exact f64 RED of +-2^32 units
+  auto apply = [&](unsigned li, int q) {
     if (!HAS_CNT || q != 0) {
-      const unsigned old = atomicAdd(table + li, (unsigned)q);
-      const int net = (q >> 31) + (int)(old + (unsigned)q < old);
-      if (net) red_add_f64_hint(p.t.t0f + (((long long)li << LOGC) | me), net > 0 ? hi_unit : -hi_unit, pol);
+      unsigned old;
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(table_s + li * 4u), "r"((unsigned)q) : "memory");
+      if ((old + (unsigned)q < old) != (q < 0))
+        atomicAdd(p.t.t0f + ((li << LOGC) | me), q >= 0 ? hi_unit : -hi_unit);
     }
     if (HAS_CNT) {
       const int sh = (int)(li & 1u) << 4; const unsigned wi = li >> 1;
@@ -194,131 +203,123 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
       reds_add_u32(cnt_sbase + wi * 4, 1u << sh);
     }
   };
-  auto global_add = [&](long long g, float x, bool with_count) {   // out-of-window values, slot-less groups, overflow records
-    if ((__float_as_uint(x) & 0x7fffffffu) != 0u) red_add_f64_hint(p.t.t0f + g, (double)x, pol);
-    if (HAS_CNT && with_count) {
-      if (p.want_cnt) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol);
-      if (p.want_b1) p.t.b1[g] = 1;
-    }
+  auto global_count = [&](long long g) {
+    if (p.want_cnt) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, l2_evict_last_policy());
+    if (p.want_b1) p.t.b1[g] = 1;
   };
-  auto consume = [&](long long ph) {                           // apply what the peers sent me in phase ph
-    const unsigned b = (unsigned)ph & 1u, par = (unsigned)(ph >> 1) & 1u;
+  auto consume = [&](unsigned ph) {                            // apply what the peers sent me in phase ph
+    const unsigned b = ph & 1u, par = (ph >> 1) & 1u;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       dsm::mbar_wait(full0 + (j * 2 + b) * BAR_B, par);
       const unsigned long long* reg = inbox + ((size_t)(j * 2 + b) * TEAM_WARPS + warp) * cap;
       const unsigned cnt = (unsigned)reg[0];
-      for (unsigned i = lane; i < cnt; i += 32) {
-        const unsigned long long rec = reg[1 + i];
-        apply((unsigned)(rec >> 32), (int)(unsigned)rec);
+      if (!(p.dbg & 2)) {
+        for (unsigned i = lane; i < cnt; i += 32) {
+          const unsigned long long rec = reg[1 + i];
+          apply((unsigned)(rec >> 32), (int)(unsigned)rec);
+        }
       }
       __syncwarp();
-      // region j came from CTA (me - j - 1) % C = peer P - 1 - j; its "empty" barrier for ME is its index j
-      if (lane == 0) dsm::remote_arrive_relaxed(rbase[P - 1 - j] + empty0 + (j * 2 + b) * BAR_B);
+      if (lane == 0) dsm::remote_arrive_relaxed(rempty0[j] + b * BAR_B);   // tell the sender of region j its buffer b is free
     }
   };
 
   // ---- main loop: phase = 128 elements per warp ------------------------------------------------------------------
-  // raw loads of the next phase stay in flight while the current one is worked on
-  long long g_raw[4]; float x_cur[4]; unsigned g_cur[4]; bool have_cur;
-  auto load = [&](long long vv, long long (&g)[4], float (&x)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { g[k] = 0; x[k] = 0.f; }
+  // the raw loads of the next phase stay in flight while the current one is worked on
+  int4 l0, l1, av;                                             // current vector: 4 labels (two 16-byte halves for int64), 4 values
+  auto load = [&](long long vv, int4& a0, int4& a1, int4& xv) {
+    a0 = make_int4(0, 0, 0, 0); a1 = a0; xv = a0;
     if (vv < nvec) {
-      LabelVec<LT>::load(p.labels, vv, g);
-      const int4 av = ldg_stream16((const int4*)p.a + vv);
-      x[0] = __int_as_float(av.x); x[1] = __int_as_float(av.y); x[2] = __int_as_float(av.z); x[3] = __int_as_float(av.w);
+      if (sizeof(LT) == 8) { a0 = ldg_stream16((const int4*)p.labels + 2 * vv); a1 = ldg_stream16((const int4*)p.labels + 2 * vv + 1); }
+      else a0 = ldg_stream16((const int4*)p.labels + vv);
+      xv = ldg_stream16((const int4*)p.a + vv);
     }
   };
-  // labels -> 32 bits (size < 2^31): 0xffffffff marks a label outside [0, size)
-  auto narrow = [&](const long long (&g)[4], unsigned (&o)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = (unsigned long long)g[k] < (unsigned long long)p.size ? (unsigned)g[k] : 0xffffffffu;
-  };
-  load(v, g_raw, x_cur);
-  narrow(g_raw, g_cur);
-  have_cur = v < nvec;
-  for (long long ph = 0; ph < nphase; ++ph) {
-    long long g_nxt[4]; float x_nxt[4];
-    load(v + grid_vecs, g_nxt, x_nxt);
-    const unsigned b = (unsigned)ph & 1u;
+  load(v, l0, l1, av);
+  const unsigned nph = (unsigned)nphase;
+  for (unsigned ph = 0; ph < nph; ++ph) {
+    int4 n0, n1, nv;
+    load(v + grid_vecs, n0, n1, nv);
+    const unsigned b = ph & 1u;
     if (ph >= 2) {                                             // buffer b is free once the peers applied phase ph - 2
-      const unsigned par = (unsigned)((ph >> 1) - 1) & 1u;
+      const unsigned par = ((ph >> 1) - 1u) & 1u;
 #pragma unroll
       for (int j = 0; j < P; ++j) dsm::mbar_wait(empty0 + (j * 2 + b) * BAR_B, par);
     }
-    unsigned sent[P];
+    unsigned dst[P], dbar[P], sent[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) sent[j] = 0;
+    for (int j = 0; j < P; ++j) { dst[j] = dst0[j] + b * buf_stride; dbar[j] = dbar0[j] + b * BAR_B; sent[j] = 0; }
+    // labels as 32-bit words; for int64 labels all four high words must be zero or the vector takes the slow look
+    unsigned glo[4], hv;
+    if (sizeof(LT) == 8) { glo[0] = l0.x; glo[1] = l0.z; glo[2] = l1.x; glo[3] = l1.z; hv = (unsigned)(l0.y | l0.w | l1.y | l1.w); }
+    else { glo[0] = l0.x; glo[1] = l0.y; glo[2] = l0.z; glo[3] = l0.w; hv = (unsigned)(l0.x | l0.y | l0.z | l0.w) >> 31; }
+    const unsigned have = dsm::keep(v < nvec ? 1u : 0u);
+    const unsigned covv = (have != 0u && hv == 0u) ? cov_c : 0u;
+    const unsigned xb[4] = {(unsigned)av.x, (unsigned)av.y, (unsigned)av.z, (unsigned)av.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const unsigned g = g_cur[k];
-      float x = x_cur[k];
-      bool act = have_cur && g != 0xffffffffu;
-      if (have_cur && !act) bad = true;
-      if (nanskip && x != x) act = false;
-      if (square) x = x * x;
-      const unsigned ab = __float_as_uint(x) & 0x7fffffffu;
-      const bool inwin = ab - lo_bits < span_bits;
+      const unsigned g = glo[k];
+      const float x = __uint_as_float(xb[k]);
+      const unsigned ab = xb[k] & 0x7fffffffu;
+      bool fast = (ab - lo_bits < span_bits) && g < covv;
+      int q = __float2int_rn(x * scale_f);                     // exact for in-window values
       const unsigned li = g >> LOGC;
-      if (act && li >= (unsigned)cov) { global_add((long long)g, x, true); act = false; }   // no slot for this group
-      int q = 0;
-      if (inwin) q = __float2int_rn(x * scale_f);                                            // exact
-      else if (act) {
-        if (ab != 0u) red_add_f64_hint(p.t.t0f + g, (double)x, pol);                          // exact bypass
-        if (!HAS_CNT) act = false;                                                            // counts still travel (q = 0)
+      if (!fast && have != 0u) {
+        // ---- the rare cases, one element at a time (the 64-bit label is read again: it is not kept in registers) ----
+        const long long g64 = LabelVec<LT>::one(p.labels, (v << 2) + k);
+        if ((unsigned long long)g64 >= (unsigned long long)p.size) bad = 1;
+        else if (!(NANSKIP && x != x)) {
+          const bool slotted = (unsigned long long)g64 < (unsigned long long)cov_c;
+          const bool inwin = ab - lo_bits < span_bits;
+          if ((!slotted || !inwin) && ab != 0u) atomicAdd(p.t.t0f + g64, (double)x);   // exact f64 bypass
+          if (HAS_CNT) {
+            if (!slotted) global_count(g64);
+            else if (!inwin) { fast = true; q = 0; }            // the count still travels to the owner
+          }
+          if (slotted && inwin) fast = true;                   // only this vector's OTHER labels were odd
+        }
       }
-      const unsigned rel = (g - me) & (C - 1);                                                // 0: mine, j + 1: peer j
-      if (act && rel == 0u) apply(li, q);
+      const unsigned rel = (p.dbg & 1) ? 0u : ((g - me) & (C - 1));   // 0: mine, j + 1: peer j
+      if (fast && rel == 0u) apply(li, q);
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        const bool go = act && rel == (unsigned)(j + 1);
+        const bool go = fast && rel == (unsigned)(j + 1);
         const unsigned m = __ballot_sync(0xffffffffu, go);
         if (go) {
           const unsigned slot = 1u + sent[j] + __popc(m & lt_mask);
-          if (slot < (unsigned)cap) {
-            const unsigned ra = rbase[j] + in0 + (j * 2 + b) * buf_stride + slot * 8u;
-            if (XPORT == 0) dsm::st_async_rec(ra, (unsigned)q, li, rbase[j] + full0 + (j * 2 + b) * BAR_B);
-            else dsm::st_remote_rec(ra, (unsigned)q, li);
-          } else {                                                                            // buffer full: the slow exact way
-            if (inwin) red_add_f64_hint(p.t.t0f + g, (double)x, pol);
-            if (HAS_CNT) { if (p.want_cnt) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol); if (p.want_b1) p.t.b1[g] = 1; }
+          if (slot < capm) dsm::st_async_rec(dst[j] + slot * 8u, (unsigned)q, li, dbar[j]);
+          else {                                               // buffer full: the slow exact way
+            if (q != 0) atomicAdd(p.t.t0f + g, (double)x);
+            if (HAS_CNT) global_count((long long)g);
           }
         }
         sent[j] += __popc(m);
       }
     }
     // announce the phase: header {count} + one arrival per peer
-    if (XPORT != 0) __syncwarp();
     if (lane == 0) {
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        const unsigned c = min(sent[j], (unsigned)cap - 1u);
-        const unsigned ra = rbase[j] + in0 + (j * 2 + b) * buf_stride;
-        const unsigned rb = rbase[j] + full0 + (j * 2 + b) * BAR_B;
-        if (XPORT == 0) {
-          dsm::st_async_rec(ra, c, 0u, rb);
-          dsm::remote_arrive_expect_tx(rb, 8u * (c + 1u));
-        } else {
-          dsm::st_remote_rec(ra, c, 0u);
-          dsm::remote_arrive_release(rb);
-        }
+        const unsigned c = min(sent[j], capm - 1u);
+        dsm::st_async_rec(dst[j], c, 0u, dbar[j]);
+        dsm::remote_arrive_expect_tx(dbar[j], 8u * (c + 1u));
       }
     }
     if (ph >= 1) consume(ph - 1);
     v += grid_vecs;
-    narrow(g_nxt, g_cur);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) x_cur[k] = x_nxt[k];
-    have_cur = v < nvec;
+    l0 = n0; l1 = n1; av = nv;
   }
-  if (nphase >= 1) consume(nphase - 1);
+  if (nph >= 1) consume(nph - 1);
   if (blockIdx.x == 0 && threadIdx.x < (p.n & 3)) {            // ragged tail: straight to the global tables
     const long long i = (nvec << 2) + threadIdx.x;
     const long long g = LabelVec<LT>::one(p.labels, i);
-    float x = p.a[i];
-    if ((unsigned long long)g >= (unsigned long long)p.size) bad = true;
-    else if (!(nanskip && x != x)) { if (square) x = x * x; global_add(g, x, true); }
+    const float x = p.a[i];
+    if ((unsigned long long)g >= (unsigned long long)p.size) bad = 1;
+    else if (!(NANSKIP && x != x)) {
+      if ((__float_as_uint(x) & 0x7fffffffu) != 0u) red_add_f64_hint(p.t.t0f + g, (double)x, l2_evict_last_policy());
+      if (HAS_CNT) global_count(g);
+    }
   }
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = 70 + MODE;
@@ -327,7 +328,6 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
   // ---- merge my slots into the global tables: ONE RED per touched group ----------------------------------------
   for (int li = threadIdx.x; li < cov; li += TEAM_THREADS) {
     const long long g = ((long long)li << LOGC) | me;
-    if (g >= p.size) break;
     const long long resid = (long long)table[li] - 0x80000000ll;
     if (resid != 0) atomicAdd(p.t.t0f + g, (double)resid * inv_scale);
     if (HAS_CNT) {
@@ -352,19 +352,26 @@ inline int team_default_cap(int C) {
   return ((int)(1 + mean + 2.5 * sd) + 3) & ~3;
 }
 
-template <int C, class LT, int MODE, int XPORT>
+template <int C, class LT, int MODE, bool NANSKIP>
 inline int launch_team(const TeamParams& p, size_t smem, cudaStream_t st, int max_clusters = 0) {
-  auto kern = k_team<C, LT, MODE, XPORT>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess) return -30;
-  if (C > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -30;
+  auto kern = k_team<C, LT, MODE, NANSKIP>;
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dyn_smem(kern, 227 * 1024 - 64, attr_done)) return -30;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(TEAM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
   cfg.gridDim = dim3(C);
-  int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return -31; }
+  // co-resident clusters of this kernel on this device (one CTA per SM: independent of the exact table size)
+  static std::atomic<int> resident[AGC_MAX_DEVICES];
+  const int dev = current_device();
+  int nclusters = resident[dev].load(std::memory_order_relaxed);
+  if (nclusters == 0) {
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); nclusters = -1; }
+    resident[dev].store(nclusters, std::memory_order_relaxed);
+  }
+  if (nclusters < 1) return -31;
   if (max_clusters > 0 && nclusters > max_clusters) nclusters = max_clusters;
   cfg.gridDim = dim3(nclusters * C);
   AGC_COUNT_LAUNCH(1);

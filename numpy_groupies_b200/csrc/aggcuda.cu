@@ -10,6 +10,7 @@
 #include "agc_dispatch.cuh"
 #include "agc_scan.cuh"
 #include "agc_labels.cuh"
+#include "agc_dist.cuh"
 
 namespace {
 
@@ -21,25 +22,24 @@ int cuda_fail(cudaError_t e, const char* where) {
 }
 #define AGC_CUDA_OK(where) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return cuda_fail(e_, where); } while (0)
 
-int g_sm_count = 0;
-int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
-}
+int sm_count() { return agc::device_sms(); }                  // of the CURRENT device
 
+// measurement hook: one event pair per device (events belong to the device they were created on)
 bool g_profile = false;
-cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-bool g_ev_valid = false;
+struct ProfEvents { cudaEvent_t e0 = nullptr, e1 = nullptr; bool valid = false; };
+ProfEvents g_prof[agc::AGC_MAX_DEVICES];
+int g_prof_last_dev = 0;
 void prof_begin(cudaStream_t st) {
   if (!g_profile) return;
-  if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-  cudaEventRecord(g_ev0, st);
+  ProfEvents& pe = g_prof[agc::current_device()];
+  if (!pe.e0) { cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1); }
+  cudaEventRecord(pe.e0, st);
 }
-void prof_end(cudaStream_t st) { if (g_profile) { cudaEventRecord(g_ev1, st); g_ev_valid = true; } }
+void prof_end(cudaStream_t st) {
+  if (!g_profile) return;
+  const int dev = agc::current_device();
+  cudaEventRecord(g_prof[dev].e1, st); g_prof[dev].valid = true; g_prof_last_dev = dev;
+}
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -131,14 +131,16 @@ int agc_partials(const agc_request_t* r, agc_partial_t* out, int max_out) {
   auto add = [&](int64_t off, int dt, int red) { tmp[k].offset_bytes = off; tmp[k].count = r->size; tmp[k].dtype = dt; tmp[k].reduce = red; ++k; };
   const bool pass2 = r->flags & AGC_F_PASS2;
   switch (r->op) {
-    case AGC_OP_SUM: case AGC_OP_SUMSQ: add(L.t0, fl ? AGC_DT_F64 : AGC_DT_I64, 0); add(L.b1, AGC_DT_U8, 1); break;
-    case AGC_OP_PROD: add(L.t0, fl ? AGC_DT_F64 : AGC_DT_I64, 3); add(L.b1, AGC_DT_U8, 1); break;
+    // the "touched" flags only travel when the finalise step reads them (fill_value differs from the identity)
+    case AGC_OP_SUM: case AGC_OP_SUMSQ: add(L.t0, fl ? AGC_DT_F64 : AGC_DT_I64, 0); if (r->flags & AGC_F_NEED_TOUCHED) add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_PROD: add(L.t0, fl ? AGC_DT_F64 : AGC_DT_I64, 3); if (r->flags & AGC_F_NEED_TOUCHED) add(L.b1, AGC_DT_U8, 1); break;
     case AGC_OP_LEN: add(L.t1, AGC_DT_I64, 0); break;
     case AGC_OP_MEAN: add(L.t0, AGC_DT_F64, 0); add(L.t1, AGC_DT_I64, 0); break;
     case AGC_OP_VAR: if (pass2) add(L.t2, AGC_DT_F64, 0); else { add(L.t0, AGC_DT_F64, 0); add(L.t1, AGC_DT_I64, 0); } break;
-    case AGC_OP_MAX: add(L.t0, AGC_DT_I64, 1); add(L.b1, AGC_DT_U8, 1); break;
-    case AGC_OP_MIN: add(L.t0, AGC_DT_I64, 2); add(L.b1, AGC_DT_U8, 1); break;
-    case AGC_OP_MINMAX: add(L.t0, AGC_DT_I64, 1); add(L.t2, AGC_DT_I64, 2); add(L.b1, AGC_DT_U8, 1); break;
+    // float max / min tell "empty" by the key itself; integer values need the flags
+    case AGC_OP_MAX: add(L.t0, AGC_DT_I64, 1); if (!agc::dtype_is_float(r->a_dtype)) add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_MIN: add(L.t0, AGC_DT_I64, 2); if (!agc::dtype_is_float(r->a_dtype)) add(L.b1, AGC_DT_U8, 1); break;
+    case AGC_OP_MINMAX: add(L.t0, AGC_DT_I64, 1); add(L.t2, AGC_DT_I64, 2); if (!agc::dtype_is_float(r->a_dtype)) add(L.b1, AGC_DT_U8, 1); break;
     case AGC_OP_ARGMAX: if (pass2) add(L.t1, AGC_DT_I64, 2); else add(L.t0, AGC_DT_I64, 1); break;
     case AGC_OP_ARGMIN: if (pass2) add(L.t1, AGC_DT_I64, 2); else add(L.t0, AGC_DT_I64, 2); break;
     case AGC_OP_ANY: case AGC_OP_ANYNAN: add(L.b0, AGC_DT_U8, 1); add(L.b1, AGC_DT_U8, 1); break;
@@ -229,18 +231,19 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
   return 0;
 }
 
-int agc_profile_enable(int on) { g_profile = on != 0; g_ev_valid = false; return 0; }
+int agc_profile_enable(int on) { g_profile = on != 0; for (auto& pe : g_prof) pe.valid = false; return 0; }
 float agc_profile_last_ms(void) {
-  if (!g_ev_valid) return -1.f;
+  ProfEvents& pe = g_prof[g_prof_last_dev];
+  if (!pe.valid) return -1.f;
   float ms = -1.f;
-  if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
-  cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+  if (cudaEventSynchronize(pe.e1) != cudaSuccess) return -1.f;
+  cudaEventElapsedTime(&ms, pe.e0, pe.e1);
   return ms;
 }
-int64_t agc_launch_count(void) { return agc::g_launches; }
+int64_t agc_launch_count(void) { return agc::g_launches.load(); }
 int agc_tuning(int key, int value) {
   agc::tuning_defaults();
-  if (key == 6) { if (value >= 0) agc::g_scan_chain = value ? 1 : 0; return agc::scan_chain_enabled() ? 1 : 0; }
+  if (key == agc::TUNE_SCAN_CHAIN) { if (value >= 0) agc::g_scan_chain = value ? 1 : 0; return agc::scan_chain_enabled() ? 1 : 0; }
   if (key < 0 || key >= agc::TUNE_COUNT) return -1;
   if (value >= 0) agc::g_tune[key] = value;
   return agc::g_tune[key];
@@ -264,6 +267,64 @@ int agc_unpack(const void* table, int32_t elem_bytes, int64_t size, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   AGC_COUNT_LAUNCH(1), agc::k_unpack<<<grid_for(n, 256, 16), 256, 0, st>>>(table, elem_bytes, size, labels, dtype, n, out, status);
   AGC_CUDA_OK("unpack");
+  return 0;
+}
+
+int agc_pack_tables(const agc_pack_seg_t* segs, int32_t nseg, void* packed, int32_t carrier_dtype, int32_t unpack, void* stream) {
+  if (nseg < 1 || nseg > agc::PK_MAX_SEGS || !segs || !packed) return fail(-6, "agc_pack_tables: bad segment list");
+  if (carrier_dtype != AGC_DT_F64 && carrier_dtype != AGC_DT_I64) return fail(-3, "agc_pack_tables: the carrier is float64 or int64");
+  agc::PackParams p;
+  memset(&p, 0, sizeof(p));
+  long long total = 0;
+  for (int i = 0; i < nseg; ++i) {
+    if (segs[i].count < 0 || (segs[i].count > 0 && !segs[i].table)) return fail(-6, "agc_pack_tables: null table");
+    const int dt = segs[i].dtype;
+    if (dt != AGC_DT_F64 && dt != AGC_DT_I64 && dt != AGC_DT_I32 && dt != AGC_DT_U8 && dt != AGC_DT_BOOL) return fail(-3, "agc_pack_tables: table dtype");
+    p.seg[i].table = segs[i].table; p.seg[i].count = segs[i].count; p.seg[i].dtype = dt; p.seg[i].xform = segs[i].xform;
+    p.start[i] = total; total += segs[i].count;
+  }
+  p.start[nseg] = total; p.nseg = nseg; p.carrier = carrier_dtype; p.packed = packed; p.unpack = unpack != 0;
+  if (total == 0) return 0;
+  AGC_COUNT_LAUNCH(1), agc::k_pack_tables<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(p);
+  AGC_CUDA_OK("pack_tables");
+  return 0;
+}
+
+int agc_rank_fold(const void* gathered, int32_t rank, int64_t size, int32_t dtype, int32_t reduce, void* carry, void* stream) {
+  if (dtype != AGC_DT_F64 && dtype != AGC_DT_I64) return fail(-3, "agc_rank_fold: tables are float64 or int64");
+  if (reduce < 0 || reduce > 3 || rank < 0) return fail(-2, "agc_rank_fold: bad reduce / rank");
+  if (size <= 0) return 0;
+  if (!gathered || !carry) return fail(-6, "agc_rank_fold: null pointer");
+  AGC_COUNT_LAUNCH(1), agc::k_rank_fold<<<grid_for(size, 256, 8), 256, 0, (cudaStream_t)stream>>>(gathered, rank, size, dtype == AGC_DT_F64, reduce, carry);
+  AGC_CUDA_OK("rank_fold");
+  return 0;
+}
+
+int agc_apply_carry(int32_t op, const void* labels, int32_t label_dtype, int64_t n, int64_t size, void* out, int32_t out_dtype,
+                    int32_t a_dtype, const void* carry, int32_t carry_dtype, int32_t* status, void* stream) {
+  if (op < AGC_OP_CUMSUM || op > AGC_OP_CUMMIN) return fail(-2, "agc_apply_carry: op must be a running function");
+  if (n <= 0 || size <= 0) return 0;
+  if (!labels || !out || !carry) return fail(-6, "agc_apply_carry: null pointer");
+  agc::CarryParams p;
+  p.labels = labels; p.ldtype = label_dtype; p.n = n; p.size = size; p.out = out; p.out_dtype = out_dtype;
+  p.carry = carry; p.acc_f64 = carry_dtype == AGC_DT_F64;
+  p.op = op == AGC_OP_CUMSUM ? 0 : (op == AGC_OP_CUMMAX ? 1 : (op == AGC_OP_CUMMIN ? 2 : 3));
+  p.a_float = agc::dtype_is_float(a_dtype); p.a_u64 = a_dtype == AGC_DT_U64; p.status = status;
+  AGC_COUNT_LAUNCH(1), agc::k_apply_carry<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+  AGC_CUDA_OK("apply_carry");
+  return 0;
+}
+
+int agc_owner_pack(const agc_request_t* r, int64_t* carrier, int32_t unpack, void* stream) {
+  if (check_request(r)) return -1;
+  if (r->op != AGC_OP_FIRST && r->op != AGC_OP_LAST) return fail(-2, "agc_owner_pack: first / last only");
+  if (r->size <= 0) return 0;
+  if (!carrier || !r->out || !r->workspace) return fail(-6, "agc_owner_pack: null pointer");
+  const Layout L = reduce_layout(r->size);
+  agc::Tables t = tables_at(r->workspace, L);
+  AGC_COUNT_LAUNCH(1), agc::k_owner_pack<<<grid_for(r->size, 256, 8), 256, 0, (cudaStream_t)stream>>>(r->out, agc::dtype_bytes(r->out_dtype), r->size, t.t1,
+                                                                                                r->index_base, r->n, (long long*)carrier, unpack != 0);
+  AGC_CUDA_OK("owner_pack");
   return 0;
 }
 

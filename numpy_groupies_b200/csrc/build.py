@@ -31,12 +31,13 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC]
+           "-shared", "-Xcompiler", "-fPIC", "-o", OUT + ".tmp", SRC]
     if verbose:
         cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(OUT + ".tmp", OUT)                            # atomic: a snapshot of the tree never sees a half-written library
     if verbose:
         print(res.stderr)
     return OUT

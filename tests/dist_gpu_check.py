@@ -66,6 +66,48 @@ def main():
             else:
                 np.testing.assert_allclose(part, full, rtol=1e-5, atol=1e-6, err_msg=f"{func} {dist_name}")
             checked += 1
+    # ---- N -> N functions: local scan + cross-GPU carry exchange; every rank returns ITS shard ---------------------
+    big = rng.integers(-2 ** 40, 2 ** 40, n)
+    small = rng.integers(-3, 4, n)                              # products stay interesting without dying at 0 too often
+    small[small == 0] = 1
+    for labels_name, gl in (("unsorted", gidx), ("sorted", np.sort(gidx))):
+        for func, arr in (("cumsum", big), ("cummax", big), ("cummin", big), ("cumprod", small), ("cumsum", a32), ("nancumsum", a64),
+                          ("cummax", a32), ("cumsum", ai.astype(np.int32))):
+            full = aggregate(torch.from_numpy(gl).cuda(), torch.from_numpy(arr).cuda(), func=func, size=groups).cpu().numpy()
+            part = aggregate_sharded(torch.from_numpy(gl[lo:hi]).cuda(), torch.from_numpy(arr[lo:hi]).cuda(), func=func, size=groups).cpu().numpy()
+            assert part.dtype == full.dtype and part.shape == (hi - lo,), (func, part.dtype, part.shape)
+            if full.dtype.kind == "f":
+                np.testing.assert_allclose(part, full[lo:hi], rtol=1e-12 if arr.dtype == np.float64 else 1e-5,
+                                           atol=1e-9 if arr.dtype == np.float64 else 1e-3, equal_nan=True, err_msg=f"{func} {labels_name}")
+            else:
+                np.testing.assert_array_equal(part, full[lo:hi], err_msg=f"{func} {labels_name}")          # bit-exact incl. wraparound
+            checked += 1
+    # ---- Form 4 (2-D group_idx) shards along N like Form 1; Form 3 on the last axis shards along the outer dimension ----
+    g4 = rng.integers(0, 60, (2, n))
+    for func in ("sum", "mean", "max", "argmax", "first"):
+        full = aggregate(torch.from_numpy(g4).cuda(), torch.from_numpy(a64).cuda(), func="nan" + func if func in ("sum", "mean", "max", "argmax") else func,
+                         size=(60, 60)).cpu().numpy()
+        part = aggregate_sharded(torch.from_numpy(np.ascontiguousarray(g4[:, lo:hi])).cuda(), torch.from_numpy(a64[lo:hi]).cuda(),
+                                 func="nan" + func if func in ("sum", "mean", "max", "argmax") else func, size=(60, 60)).cpu().numpy()
+        assert part.shape == full.shape == (60, 60)
+        if full.dtype.kind == "f":
+            np.testing.assert_allclose(part, full, rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=f"form4 {func}")
+        else:
+            np.testing.assert_array_equal(part, full, err_msg=f"form4 {func}")
+        checked += 1
+    rows = 64 * world
+    a3 = rng.random((rows, 3000)).astype(np.float32)
+    g3 = rng.integers(0, 40, 3000)
+    r0, r1 = rank * 64, (rank + 1) * 64
+    for func in ("sum", "max", "mean", "cumsum"):
+        full = aggregate(torch.from_numpy(g3).cuda(), torch.from_numpy(a3).cuda(), func=func, size=40, axis=1).cpu().numpy()
+        part = aggregate_sharded(torch.from_numpy(g3).cuda(), torch.from_numpy(a3[r0:r1]).cuda(), func=func, size=40, axis=1).cpu().numpy()
+        if func == "cumsum":
+            np.testing.assert_allclose(part, full[r0:r1], rtol=1e-5, err_msg="form3 cumsum")
+        else:
+            assert part.shape == full.shape
+            np.testing.assert_allclose(part, full, rtol=1e-5, err_msg=f"form3 {func}")
+        checked += 1
     dist.barrier()
     if rank == 0:
         print(f"dist_gpu_check ok: {checked} functions, world={world}")

@@ -132,3 +132,136 @@ def test_two_rank_merge_matches_unsharded_oracle():
     np.testing.assert_array_equal(out["argmax"], oracle.aggregate(gidx, a, "argmax", size=SIZE, fill_value=-1))
     first_ref = oracle.aggregate(gidx, np.arange(n), "first", size=SIZE, fill_value=np.iinfo(np.int64).max)
     np.testing.assert_array_equal(out["first_idx"], first_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# the packed merge: ONE all-reduce per phase.  pack_plan() (host logic) decides how every partial table of a call rides
+# in one homogeneous buffer; k_pack_tables is emulated in numpy here, the collective is real (gloo, world size 2), and the
+# result must equal the per-table merge the library's agc_partials prescribes.
+# ------------------------------------------------------------------------------------------------
+def _np_pack(tables, xforms, status, st_x, carrier):
+    segs = [(t, xforms[i]) for i, t in enumerate(tables) if i in xforms] + [(status[:3], st_x)]
+    out = []
+    for t, xf in segs:
+        v = t.astype(np.float64 if carrier == "float64" else np.int64)
+        if xf in (_abi.PK_NEG, _abi.PK_NEGFLAG):
+            v = -v if carrier == "float64" else ~v
+        out.append(v)
+    return np.concatenate(out), segs
+
+
+def _np_unpack(packed, segs, carrier):
+    off = 0
+    for t, xf in segs:
+        v = packed[off:off + t.size]
+        off += t.size
+        if xf in (_abi.PK_NEG, _abi.PK_NEGFLAG):
+            v = -v if carrier == "float64" else ~v
+        if xf in (_abi.PK_FLAG, _abi.PK_NEGFLAG):
+            v = (v != 0)
+        t[...] = v.astype(t.dtype)
+
+
+def _fake_tables(spec, rng):
+    tabs = []
+    for dt, red in spec:
+        if dt == "float64":
+            tabs.append(rng.standard_normal(SIZE))
+        elif dt == "uint8":
+            tabs.append((rng.random(SIZE) < 0.5).astype(np.uint8))
+        else:
+            t = rng.integers(-2 ** 62, 2 ** 62, SIZE)
+            t[::5] = np.iinfo(np.int64).min                    # "empty" keys must survive the bit complement
+            t[1::7] = np.iinfo(np.int64).max
+            if red == "sum":
+                t = rng.integers(0, 1000, SIZE)
+            tabs.append(t.astype(np.int64))
+    return tabs
+
+
+_PACK_CASES = [("sum", 0, "float64"), ("sum", _abi.F_NEED_TOUCHED, "float64"), ("sum", _abi.F_NEED_TOUCHED, "int64"), ("mean", 0, "float64"),
+               ("len", 0, "float64"), ("var", _abi.F_PASS2, "float64"), ("max", 0, "float64"), ("min", 0, "int64"), ("max", 0, "int64"),
+               ("minmax", _abi.F_ACC_ONLY, "int64"), ("argmin", 0, "float64"), ("first", 0, "float64"), ("last", 0, "float64"),
+               ("any", 0, "float64"), ("all", 0, "float64"), ("prod", _abi.F_NEED_TOUCHED, "float64")]
+
+
+def _spec_for(op, flags, a_dtype):
+    lib = _abi.load()
+    req = _abi.Request()
+    req.op, req.flags, req.a_dtype, req.out_dtype = _abi.OP[op], flags, _abi.DT[a_dtype], _abi.DT[a_dtype]
+    req.size, req.n = SIZE, 10
+    dummy = C.c_int64(0)
+    req.status = C.cast(C.pointer(dummy), C.c_void_p)
+    req.index.labels = C.cast(C.pointer(dummy), C.c_void_p)
+    req.index.dtype = _abi.DT["int64"]
+    req.out = C.cast(C.pointer(dummy), C.c_void_p)
+    parts = (_abi.Partial * 6)()
+    k = lib.agc_partials(C.byref(req), parts, 6)
+    assert k > 0, _abi.last_error()
+    return [(parts[i].dtype, parts[i].reduce) for i in range(k)]
+
+
+def _pack_worker(rank, world, port, q):
+    from numpy_groupies_b200.distributed import pack_plan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ops = {"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}
+    try:
+        bad = []
+        for ci, (op, flags, a_dtype) in enumerate(_PACK_CASES):
+            codes = _spec_for(op, flags, a_dtype)
+            spec = [(_abi.DT_NAME[d], _abi.REDUCE_NAMES[r]) for d, r in codes]
+            rng = np.random.default_rng(1000 * ci + rank)
+            tabs = _fake_tables(spec, rng)
+            status = np.array([rank == 1 and ci % 2 == 0, 0, 0, 55, 0, 0, 0, 0], dtype=np.int32)
+            # reference: one collective per table + one for the status
+            ref = [torch.from_numpy(t.copy()) for t in tabs]
+            merge_tables([(t, red) for t, (_, red) in zip(ref, spec)])
+            st_ref = torch.from_numpy(status.copy())
+            dist.all_reduce(st_ref, op=dist.ReduceOp.MAX)
+            # packed: ONE collective (products ride alone)
+            carrier, red, xforms, st_x, product = pack_plan(codes)
+            got = [t.copy() for t in tabs]
+            st_got = status.copy()
+            for i in product:
+                tp = torch.from_numpy(got[i]); dist.all_reduce(tp, op=dist.ReduceOp.PRODUCT)
+            cname = _abi.DT_NAME[carrier]
+            packed, segs = _np_pack(got, xforms, st_got, st_x, cname)
+            tpk = torch.from_numpy(packed)
+            dist.all_reduce(tpk, op=ops[red])
+            _np_unpack(tpk.numpy(), segs, cname)
+            for i, (t, r_) in enumerate(zip(got, ref)):
+                r_np = r_.numpy()
+                same = np.allclose(t, r_np, rtol=1e-12, atol=0) if t.dtype == np.float64 else np.array_equal(t != 0 if spec[i][0] == "uint8" else t, r_np != 0 if spec[i][0] == "uint8" else r_np)
+                if not same:
+                    bad.append((op, a_dtype, i, spec[i]))
+            if bool(st_got[0]) != bool(st_ref.numpy()[0]) or st_got[3] != 55:
+                bad.append((op, a_dtype, "status", st_got.tolist()))
+        if rank == 0:
+            q.put(bad)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_merge_is_one_collective_and_equals_per_table_merge():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pack_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    bad = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert bad == []
+
+
+def test_partials_drop_unread_tables():
+    """The "touched" flags only travel when the finalise step reads them (round-1 merged 100 KB of them for nothing)."""
+    f64, i64, u8 = _abi.DT["float64"], _abi.DT["int64"], _abi.DT["uint8"]
+    assert _spec_for("sum", 0, "float64") == [(f64, 0)]
+    assert _spec_for("sum", _abi.F_NEED_TOUCHED, "float64") == [(f64, 0), (u8, 1)]
+    assert _spec_for("max", 0, "float64") == [(i64, 1)]
+    assert _spec_for("max", 0, "int64") == [(i64, 1), (u8, 1)]

@@ -144,14 +144,13 @@ int run_xport(int phases, int K) {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("{\"error\": \"%s at %s:%d\"}\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
-template <int C, int MODE, int XPORT>
-int launch(const TeamParams& p, size_t smem, int max_clusters) { return launch_team<C, long long, MODE, XPORT>(p, smem, 0, max_clusters); }
+template <int C, int MODE, int NS>
+int launch(const TeamParams& p, size_t smem, int max_clusters) { return launch_team<C, long long, MODE, NS != 0>(p, smem, 0, max_clusters); }
 
 int dispatch(int C, int mode, int xport, const TeamParams& p, size_t smem, int mc) {
 #define ONE(C_, M_, X_) if (C == C_ && mode == M_ && xport == X_) return launch<C_, M_, X_>(p, smem, mc);
   ONE(2, 0, 0) ONE(2, 0, 1) ONE(2, 1, 0) ONE(2, 1, 1)
   ONE(4, 0, 0) ONE(4, 0, 1) ONE(4, 1, 0) ONE(4, 1, 1)
-  ONE(8, 0, 0) ONE(8, 1, 0)
 #undef ONE
   return -99;
 }
@@ -174,10 +173,11 @@ int main(int argc, char** argv) {
   const int reps = argc > 8 ? atoi(argv[8]) : 5;
   const int mc = argc > 9 ? atoi(argv[9]) : 0;
   const int dist = argc > 10 ? atoi(argv[10]) : 0;
+  const int dbg = argc > 11 ? atoi(argv[11]) : 0;
   if (cap <= 0) cap = team_default_cap(C);
   const long long n = (1ll << log2n) + (log2n < 30 ? 3 : 0);                 // ragged tail on the small cases
   const size_t fixed = team_smem_bytes(C, mode, 0, cap);
-  long long cov_need = (G + C - 1) / C;
+  long long cov_need = G / C;                                                  // cov * C <= size (the kernel relies on it)
   long long cov_max = mode == TM_SUM ? (budget - (long long)fixed - 16) / 4 : (budget - (long long)fixed - 16) / 6;
   const int cov = (int)(cov_need < cov_max ? cov_need : cov_max);
   const size_t smem = team_smem_bytes(C, mode, cov, cap);
@@ -196,7 +196,7 @@ int main(int argc, char** argv) {
   memset(&p, 0, sizeof(p));
   p.labels = labels; p.a = a; p.n = n; p.size = G;
   p.t.t0f = s_out; p.t.t0i = (long long*)s_out; p.t.t1 = c_out; p.t.b1 = b1; p.status = status;
-  p.flags = 0; p.square = 0; p.want_cnt = 1; p.want_b1 = 0; p.cov = cov; p.cap = cap; p.choose = nullptr; p.want = 0;
+  p.flags = 0; p.want_cnt = 1; p.want_b1 = 0; p.cov = cov; p.cap = cap; p.choose = nullptr; p.want = 0; p.dbg = dbg;
 
   int ncl = dispatch(C, mode, xport, p, smem, mc);
   if (ncl < 0) { printf("{\"error\": \"launch rc %d\", \"smem\": %zu}\n", ncl, smem); return 1; }
@@ -218,9 +218,9 @@ int main(int argc, char** argv) {
     best = ms < best ? ms : best; tot += ms;
   }
   printf("{\"C\": %d, \"xport\": %d, \"mode\": %d, \"log2n\": %d, \"groups\": %lld, \"dist\": %d, \"cov\": %d, \"cov_need\": %lld, \"cap\": %d, \"smem\": %zu, "
-         "\"clusters\": %d, \"max_rel_err\": %.3e, \"count_mismatch\": %llu, \"bad\": %d, \"regime\": %d, \"ms_best\": %.4f, \"ms_mean\": %.4f, "
+         "\"dbg\": %d, \"clusters\": %d, \"max_rel_err\": %.3e, \"count_mismatch\": %llu, \"bad\": %d, \"regime\": %d, \"ms_best\": %.4f, \"ms_mean\": %.4f, "
          "\"gelem_s\": %.1f, \"frac_6557\": %.4f}\n",
-         C, xport, mode, log2n, G, dist, cov, cov_need, cap, smem, ncl, h_cmp[0], mism, h_status[0], h_status[3], best, tot / reps,
+         C, xport, mode, log2n, G, dist, cov, cov_need, cap, smem, dbg, ncl, h_cmp[0], mism, h_status[0], h_status[3], best, tot / reps,
          (double)n / best * 1e-6, ((double)n * 12 + G * 4) / best * 1e-6 / 6557.1);
   return 0;
 }
