@@ -187,6 +187,13 @@ int         agc_rank_fold(const void* gathered, int32_t rank, int64_t size, int3
 int         agc_apply_carry(int32_t op, const void* labels, int32_t label_dtype, int64_t n, int64_t size, void* out, int32_t out_dtype,
                             int32_t a_dtype, const void* carry, int32_t carry_dtype, int32_t* status, void* stream);
 
+/* deterministic fixed-order mode: instead of agc_aggregate(req | AGC_F_ACC_ONLY), fill the accumulator tables of a floating
+ * sum / sumofsquares / mean / var(std) / prod by walking every group's elements in their original order (`order`, `offsets`
+ * from agc_group_order): one warp per group, lane-strided sequential f64 additions, fixed butterfly across the lanes.  The
+ * result's bits depend on the input alone.  With AGC_F_PASS2 only the second pass of var / std runs (T0 holds the merged
+ * means).  Finalise with agc_aggregate(req | AGC_F_FIN_ONLY). */
+int         agc_ordered_accumulate(const agc_request_t* req, const int64_t* order, const int64_t* offsets, void* stream);
+
 /* first / last over shards (after the index tables were merged and req was finalised with AGC_F_FIN_ONLY): pack writes
  * carrier[g] = bits of out[g] where THIS shard holds the group's winning element, else 0 (one int64 SUM all-reduce hands
  * every rank the owner's bits); unpack stores them into out[g] for every non-empty group. */
@@ -211,7 +218,7 @@ int64_t     agc_launch_count(void);
  *   key 6  sorted-label scans: 1 single-pass chained scan with warp-parallel look-back (default), 0 the three-kernel
  *          reduce / scan-tiles / apply variant
  *   key 7  sums / means on tables larger than one SM: thread-block clusters of this many SMs (2 | 4) own the table together
- *          and exchange records over DSMEM (k_team); 0 = partial table + global RED (the round-1 kernels).  Default 2
+ *          and exchange records over DSMEM (k_team); 0 = partial table + global RED (default: the exchange measured slower than the REDs it saves)
  *   key 8  k_team runs while at most this percentage of the groups stays without a slot (default 60) */
 int         agc_tuning(int key, int value);
 

@@ -55,7 +55,7 @@ EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_part
            "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order",
            "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count", "agc_tuning",
            "agc_label_scan_workspace_bytes", "agc_label_scan", "agc_mark_present", "agc_multi_arange",
-           "agc_pack_tables", "agc_rank_fold", "agc_apply_carry", "agc_owner_pack")
+           "agc_pack_tables", "agc_rank_fold", "agc_apply_carry", "agc_owner_pack", "agc_ordered_accumulate")
 
 _lib = None
 
@@ -102,6 +102,8 @@ def load():
     lib.agc_multi_arange.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.agc_pack_tables.restype = C.c_int
     lib.agc_pack_tables.argtypes = [C.POINTER(PackSeg), C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.agc_ordered_accumulate.restype = C.c_int
+    lib.agc_ordered_accumulate.argtypes = [C.POINTER(Request), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.agc_owner_pack.restype = C.c_int
     lib.agc_owner_pack.argtypes = [C.POINTER(Request), C.c_void_p, C.c_int32, C.c_void_p]
     lib.agc_rank_fold.restype = C.c_int

@@ -18,6 +18,10 @@ Extra keyword arguments beyond the reference's (it already takes ``**kwargs``):
                       call asynchronous; bad labels are then ignored silently.
   assume_sorted=False promise non-decreasing flat labels (N->N functions skip the sort; verified).
   fast=True           allow the shared-memory fast kernels (False forces the general path).
+  deterministic=False fixed-order mode: floating sum / mean / var / std / sumofsquares / prod add every group's elements in
+                      their original order (device radix sort by group, one warp per group, fixed butterfly) -- the same
+                      bits on every run; float scans keep the three-kernel variant.  Slower (it sorts); integer, min / max,
+                      arg*, first / last and count results never depend on the order.
 """
 from __future__ import annotations
 
@@ -220,6 +224,7 @@ def _as_user_tensor(dev):
 _DEVICE_OPS = {"sum", "prod", "len", "last", "first", "all", "any", "min", "max", "argmax", "argmin", "mean",
                "sumofsquares", "var", "std", "allnan", "anynan", "cumsum", "cumprod", "cummax", "cummin", "sort"}
 _N_TO_N = {"cumsum", "cumprod", "cummax", "cummin", "sort"}
+_ORDERED_OPS = {"sum", "sumofsquares", "mean", "var", "std", "prod"}     # what deterministic=True re-routes (floating a)
 _COMPUTE_AS = {"float16": np.float32}          # dtypes the kernels do not load natively
 
 
@@ -260,6 +265,7 @@ def _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, kwargs, r
     c.check = kwargs.pop("check", True)
     c.assume_sorted = bool(kwargs.pop("assume_sorted", False))
     c.fast = bool(kwargs.pop("fast", True))
+    c.deterministic = bool(kwargs.pop("deterministic", False))
 
     # --- what kind of inputs ------------------------------------------------------------------
     c.device_mode = _is_tensor(group_idx) or _is_tensor(a)
@@ -387,6 +393,8 @@ def _prepare(group_idx, a, func, size, fill_value, order, dtype, axis, kwargs, r
         flags |= _abi.F_ASSUME_SORTED
     if not c.fast:
         flags |= _abi.F_NO_FAST
+    if c.deterministic:
+        flags |= _abi.F_DETERMINISTIC
     if out_dtype == np.dtype(object) or _dtname(out_dtype) not in _abi.DT and _dtname(out_dtype) != "float16":
         raise NotImplementedError(f"output dtype {out_dtype} is not supported by aggregate_cuda")
     if base in _N_TO_N and plan.ndim_idx > 1 and int(np.prod(plan.out_shape, dtype=np.int64)) != plan.n:
@@ -528,7 +536,17 @@ def _run_device(c):
             raise RuntimeError(_abi.last_error())
         ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
         req.workspace, req.workspace_bytes = ws.data_ptr(), ws_bytes
-        rc = lib.agc_aggregate(C.byref(req), _stream_ptr(device))
+        ordered = (c.deterministic and base in _ORDERED_OPS and vals is not None and np.issubdtype(a_dt, np.floating) and plan.n > 0)
+        if ordered:
+            # fixed-order mode: group the element positions (stable radix sort), then one warp per group adds in element order
+            order_t, offsets_t = _group_order(c)
+            req.flags = c.flags | _abi.F_ACC_ONLY
+            rc = lib.agc_ordered_accumulate(C.byref(req), order_t.data_ptr(), offsets_t.data_ptr(), _stream_ptr(device))
+            if rc == 0:
+                req.flags = c.flags | _abi.F_FIN_ONLY
+                rc = lib.agc_aggregate(C.byref(req), _stream_ptr(device))
+        else:
+            rc = lib.agc_aggregate(C.byref(req), _stream_ptr(device))
         if rc:
             msg = _abi.last_error()
             if rc == -20:

@@ -104,8 +104,9 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
 //                         beyond that it grows to 226 KB (default 10; measured crossover 9-17 %, scripts/uncov_sweep.py)
 //   key 6  (agc_scan.cuh) sorted-label scans: chained single pass (1, default) or the three-kernel variant (0)
 //   key 7  AGC_TEAM       sums / means on tables larger than one SM: thread-block clusters of this many SMs own the table
-//                         together and exchange records over DSMEM (k_team, agc_team.cuh); 0 = partial table + global RED
-//                         as in round 1.  Default 2.
+//                         together and exchange records over DSMEM (k_team, agc_team.cuh); 0 = partial table + global RED.
+//                         Default 0: measured on B200, a record that travels through the exchange costs ~9 issue clocks per
+//                         SM (compaction, st.async, receive loop) where a global RED costs ~2.6 (profiles/r02_team_*.jsonl)
 //   key 8  AGC_TEAM_MAXU  k_team runs while at most this percentage of the groups stays without a slot (default 60)
 enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_UNCOV = 5, TUNE_SCAN_CHAIN = 6, TUNE_TEAM = 7,
        TUNE_TEAM_MAXU = 8, TUNE_COUNT = 9 };
@@ -120,8 +121,8 @@ inline void tuning_defaults_once() {
   e = getenv("AGC_SMEM2");      g_tune[TUNE_SMEM2] = e ? atoi(e) : 99200;
   e = getenv("AGC_UNCOV_PCT");  g_tune[TUNE_UNCOV] = e ? atoi(e) : 10;
   g_tune[TUNE_SCAN_CHAIN] = 1;                                 // lives in agc_scan.cuh (agc_tuning forwards key 6)
-  e = getenv("AGC_TEAM");       g_tune[TUNE_TEAM] = e ? atoi(e) : 2;
-  if (g_tune[TUNE_TEAM] != 0 && g_tune[TUNE_TEAM] != 2 && g_tune[TUNE_TEAM] != 4) g_tune[TUNE_TEAM] = 2;
+  e = getenv("AGC_TEAM");       g_tune[TUNE_TEAM] = e ? atoi(e) : 0;
+  if (g_tune[TUNE_TEAM] != 0 && g_tune[TUNE_TEAM] != 2 && g_tune[TUNE_TEAM] != 4) g_tune[TUNE_TEAM] = 0;
   e = getenv("AGC_TEAM_MAXU");  g_tune[TUNE_TEAM_MAXU] = e ? atoi(e) : 60;
 }
 inline void tuning_defaults() { static std::once_flag once; std::call_once(once, tuning_defaults_once); }
@@ -389,7 +390,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
         TeamParams tp;
         tp.labels = r->index.labels; tp.a = (const float*)r->a; tp.n = r->n; tp.size = r->size; tp.t = t; tp.status = r->status;
         tp.flags = r->flags; tp.want_cnt = p.want_cnt; tp.want_b1 = p.want_b1; tp.cov = (int)cov; tp.cap = tcap;
-        tp.choose = probe ? choose : nullptr; tp.want = 0; tp.dbg = 0;
+        tp.choose = probe ? choose : nullptr; tp.want = 0;
         const size_t tsmem = team_smem_bytes(team_c, tmode, (int)cov, tcap);
         const int trc = i64 ? launch_team_lt<long long>(team_c, tmode, nanskip, tp, tsmem, st) : launch_team_lt<int>(team_c, tmode, nanskip, tp, tsmem, st);
         if (trc > 0) team_done = true;

@@ -166,3 +166,79 @@ __global__ void k_owner_pack(void* out, int elem_bytes, long long size, const lo
 }
 
 }  // namespace agc
+
+// ---------------------------------------------------------------------------------------------
+// deterministic fixed-order mode (north_star: "optional deterministic fixed-order mode")
+// ---------------------------------------------------------------------------------------------
+// Floating sums / means / variances / products whose bits do not depend on how the hardware schedules atomics: the
+// elements are first ordered by group with the stable radix sort (agc_group_order: order[] + CSR offsets[]), then ONE WARP
+// per group walks its elements in their original order -- lane l takes elements l, l + 32, ... of the group and adds them
+// one after the other in f64, the 32 lane totals are combined by a fixed butterfly.  The order of every addition is a
+// function of the group's element list alone: same input, same bits, on every run and on every B200.  var / std run the
+// reference's second pass (aggregate_numpy.py:180-187) the same way.  Results land in the ordinary accumulator tables and
+// are finalised by k_finalize like any other call.
+namespace agc {
+
+struct OrderedParams {
+  const void* a; int a_dtype;
+  const long long* order; const long long* offsets;
+  long long size;
+  Tables t;
+  int op, flags;
+};
+
+__device__ __forceinline__ double ord_load(const void* a, int dt, long long i) {
+  return dt == AGC_DT_F32 ? (double)((const float*)a)[i] : ((const double*)a)[i];
+}
+__device__ __forceinline__ double warp_fold_add(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_fold_mul(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_ordered_accumulate(const OrderedParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool nanskip = p.flags & AGC_F_NANSKIP;
+  const bool pass2_only = p.flags & AGC_F_PASS2;
+  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < p.size; g += warps) {
+    const long long lo = p.offsets[g], hi = p.offsets[g + 1];
+    double acc = p.op == AGC_OP_PROD ? 1.0 : 0.0;
+    long long cnt = 0;
+    if (!pass2_only) {
+      for (long long k = lo + lane; k < hi; k += 32) {
+        const double v = ord_load(p.a, p.a_dtype, p.order[k]);
+        if (nanskip && v != v) continue;
+        ++cnt;
+        if (p.op == AGC_OP_PROD) acc *= v;
+        else if (p.op == AGC_OP_SUMSQ) { const double s = p.a_dtype == AGC_DT_F32 ? (double)((float)v * (float)v) : v * v; acc += s; }   // square in a.dtype
+        else acc += v;
+      }
+      acc = p.op == AGC_OP_PROD ? warp_fold_mul(acc) : warp_fold_add(acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) { p.t.t0f[g] = acc; p.t.t1[g] = cnt; p.t.b1[g] = cnt > 0; }
+    } else {
+      acc = p.t.t0f[g]; cnt = p.t.t1[g];                      // merged over the ranks by the caller
+    }
+    if (p.op == AGC_OP_VAR) {
+      const double mean = pass2_only ? acc : acc / (double)cnt;   // pass2_only: T0 already holds the mean (k_means_inplace)
+      double m2 = 0.0;
+      for (long long k = lo + lane; k < hi; k += 32) {
+        const double v = ord_load(p.a, p.a_dtype, p.order[k]);
+        if (nanskip && v != v) continue;
+        const double d = v - mean;
+        m2 += d * d;
+      }
+      m2 = warp_fold_add(m2);
+      if (lane == 0) p.t.t2[g] = m2;
+    }
+  }
+}
+
+}  // namespace agc

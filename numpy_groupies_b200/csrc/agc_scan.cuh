@@ -550,27 +550,43 @@ template <class A> __device__ __forceinline__ A scan_unbits(unsigned long long b
 template <> __device__ __forceinline__ long long scan_unbits<long long>(unsigned long long b) { return (long long)b; }
 template <> __device__ __forceinline__ double scan_unbits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
 
-// called by the 32 threads of warp 0; returns the carry into tile t (t > 0): the running value at the end of tile t - 1
+// called by the 32 threads of warp 0; returns the carry into tile t (t > 0): the running value at the end of tile t - 1.
+// A round fetches LB_W windows of 32 descriptors at once (lane l: tiles t-1-l, t-33-l, ...): the chain of published
+// prefixes then advances 32 * LB_W tiles per L2 round trip.  With one window per round it advanced 32 tiles per ~0.7 us
+// while a 6.5 TB/s stream retires ~130 tiles of 2048 elements per us -- the scan ran at the pace of its look-back.
+constexpr int LB_W = 4;
 template <class A, int OP>
 __device__ __forceinline__ A chain_lookback(const unsigned long long* desc, int t, int lane) {
   A acc = A(0); bool have = false;
   int look = t - 1 - lane;
   for (;;) {
-    unsigned long long m = 2, xb = 0;                          // lanes past tile 0 never matter (tile 0 is a terminator)
-    if (look >= 0) { do { desc_load(desc + 2 * (long long)look, m, xb); } while ((m & 3ull) == 0ull); }
-    const bool term = (m & 3ull) == 2ull || (m & 0x100ull) != 0ull;
-    const unsigned tb = __ballot_sync(0xffffffffu, term);
-    const int first = tb ? __ffs((int)tb) - 1 : 32;            // nearest terminator in the window
-    A x = scan_unbits<A>(xb);
+    unsigned long long m[LB_W], xb[LB_W];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {                         // lane i ends with the fold of lanes [i, first], farthest first
-      const A y = __shfl_down_sync(0xffffffffu, x, o);
-      if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+    for (int w = 0; w < LB_W; ++w) {                           // all windows of the round in flight together
+      m[w] = 2ull; xb[w] = 0ull;                               // tiles before tile 0 never matter (tile 0 is a terminator)
+      if (look - 32 * w >= 0) desc_load(desc + 2 * (long long)(look - 32 * w), m[w], xb[w]);
     }
-    const A win = __shfl_sync(0xffffffffu, x, 0);
-    acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
-    if (tb) break;
-    look -= 32;
+    bool done = false;
+#pragma unroll
+    for (int w = 0; w < LB_W; ++w) {
+      if (done) break;
+      const int lk = look - 32 * w;
+      while (lk >= 0 && (m[w] & 3ull) == 0ull) desc_load(desc + 2 * (long long)lk, m[w], xb[w]);   // not published yet: wait for it
+      const bool term = (m[w] & 3ull) == 2ull || (m[w] & 0x100ull) != 0ull;
+      const unsigned tb = __ballot_sync(0xffffffffu, term);
+      const int first = tb ? __ffs((int)tb) - 1 : 32;          // nearest terminator in this window
+      A x = scan_unbits<A>(xb[w]);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {                       // lane i ends with the fold of lanes [i, first], farthest first
+        const A y = __shfl_down_sync(0xffffffffu, x, o);
+        if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+      }
+      const A win = __shfl_sync(0xffffffffu, x, 0);
+      acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
+      if (tb) done = true;
+    }
+    if (done) break;
+    look -= 32 * LB_W;
   }
   return acc;
 }
@@ -916,7 +932,9 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
   const int ntiles = (int)((p.n + SG_TILE - 1) / SG_TILE);
   unsigned char* tf = (unsigned char*)(ws + L.tile_f); A* tx = (A*)(ws + L.tile_x);
   unsigned char* cf = (unsigned char*)(ws + L.carry_f); A* cx = (A*)(ws + L.carry_x);
-  if (scan_chain_enabled()) {          // one pass, 24 B/element: tile descriptors + warp-parallel look-back
+  // (deterministic mode keeps the three-kernel variant: its order of floating additions does not depend on which tiles
+  //  had published a prefix when a look-back came by)
+  if (scan_chain_enabled() && !(p.flags & AGC_F_DETERMINISTIC)) {          // one pass, 24 B/element: tile descriptors + warp-parallel look-back
     cudaMemsetAsync(ws + L.desc, 0, (size_t)ntiles * 16, st);
     AGC_COUNT_LAUNCH(1), k_seg_scan_direct<A, OP, LT, 2><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, (A*)(ws + L.desc), nullptr, nullptr);
     return;

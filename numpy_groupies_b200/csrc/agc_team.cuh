@@ -37,7 +37,6 @@ struct TeamParams {
   int cap;              // 8-byte record slots per (peer, buffer, warp), slot 0 is the header {count}
   const int* choose;    // device word written by k_skew_probe; run iff *choose == want (NULL: always)
   int want;
-  int dbg;              // measurements only (ubench/team_probe): 1 every element is treated as mine (no exchange), 2 records are received but not applied
 };
 
 namespace dsm {
@@ -189,19 +188,21 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
     }
   };
   // a record (or an own element) into MY table: one native ATOMS.ADD; a carry / borrow out of the 32-bit word (the add
-  // wrapped although q >= 0, or did not although q < 0) is forwarded at once as an exact f64 RED of +-2^32 units
-  auto apply = [&](unsigned li, int q) {
-    if (!HAS_CNT || q != 0) {
-      unsigned old;
-      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(table_s + li * 4u), "r"((unsigned)q) : "memory");
-      if ((old + (unsigned)q < old) != (q < 0))
-        atomicAdd(p.t.t0f + ((li << LOGC) | me), q >= 0 ? hi_unit : -hi_unit);
-    }
-    if (HAS_CNT) {
-      const int sh = (int)(li & 1u) << 4; const unsigned wi = li >> 1;
-      if (((*(volatile unsigned*)(cnt16 + wi) >> sh) & 0xffffu) >= 0x8000u) repair(wi, sh, ((long long)li << LOGC) | me);
-      reds_add_u32(cnt_sbase + wi * 4, 1u << sh);
-    }
+  // wrapped although q >= 0, or did not although q < 0) is forwarded at once as an exact f64 RED of +-2^32 units.
+  // Issue and check are separate steps: a warp issues the ATOMS of a whole batch before it looks at the first old value
+  // (the kernel is bound by the latency of its dependent steps, not by issue slots).
+  auto apply_issue = [&](unsigned li, int q) -> unsigned {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(table_s + li * 4u), "r"((unsigned)q) : "memory");
+    return old;
+  };
+  auto apply_check = [&](unsigned li, int q, unsigned old) {
+    if ((old + (unsigned)q < old) != (q < 0)) atomicAdd(p.t.t0f + ((li << LOGC) | me), q >= 0 ? hi_unit : -hi_unit);
+  };
+  auto count_one = [&](unsigned li) {
+    const int sh = (int)(li & 1u) << 4; const unsigned wi = li >> 1;
+    if (((*(volatile unsigned*)(cnt16 + wi) >> sh) & 0xffffu) >= 0x8000u) repair(wi, sh, ((long long)li << LOGC) | me);
+    reds_add_u32(cnt_sbase + wi * 4, 1u << sh);
   };
   auto global_count = [&](long long g) {
     if (p.want_cnt) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, l2_evict_last_policy());
@@ -214,10 +215,17 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
       dsm::mbar_wait(full0 + (j * 2 + b) * BAR_B, par);
       const unsigned long long* reg = inbox + ((size_t)(j * 2 + b) * TEAM_WARPS + warp) * cap;
       const unsigned cnt = (unsigned)reg[0];
-      if (!(p.dbg & 2)) {
-        for (unsigned i = lane; i < cnt; i += 32) {
-          const unsigned long long rec = reg[1 + i];
-          apply((unsigned)(rec >> 32), (int)(unsigned)rec);
+      {
+        constexpr int ROUNDS = 3;                              // cap <= 97 records per buffer (host side)
+        unsigned long long rec[ROUNDS]; unsigned old[ROUNDS];
+#pragma unroll
+        for (int t = 0; t < ROUNDS; ++t) { const unsigned i = lane + 32u * t; rec[t] = i < cnt ? reg[1 + i] : 0ull; }
+#pragma unroll
+        for (int t = 0; t < ROUNDS; ++t) { old[t] = 0u; if ((unsigned)rec[t] != 0u) old[t] = apply_issue((unsigned)(rec[t] >> 32), (int)(unsigned)rec[t]); }
+#pragma unroll
+        for (int t = 0; t < ROUNDS; ++t) {
+          if ((unsigned)rec[t] != 0u) apply_check((unsigned)(rec[t] >> 32), (int)(unsigned)rec[t], old[t]);
+          if (HAS_CNT && lane + 32u * t < cnt) count_one((unsigned)(rec[t] >> 32));
         }
       }
       __syncwarp();
@@ -257,6 +265,8 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
     const unsigned have = dsm::keep(v < nvec ? 1u : 0u);
     const unsigned covv = (have != 0u && hv == 0u) ? cov_c : 0u;
     const unsigned xb[4] = {(unsigned)av.x, (unsigned)av.y, (unsigned)av.z, (unsigned)av.w};
+    // ---- step 1: classify the four elements (fixed-point value, owner, slot) ----
+    int q4[4]; unsigned rel4[4]; unsigned fastm = 0u;          // bit k of fastm: element k goes into a table of the cluster
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const unsigned g = glo[k];
@@ -264,15 +274,15 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
       const unsigned ab = xb[k] & 0x7fffffffu;
       bool fast = (ab - lo_bits < span_bits) && g < covv;
       int q = __float2int_rn(x * scale_f);                     // exact for in-window values
-      const unsigned li = g >> LOGC;
       if (!fast && have != 0u) {
-        // ---- the rare cases, one element at a time (the 64-bit label is read again: it is not kept in registers) ----
-        const long long g64 = LabelVec<LT>::one(p.labels, (v << 2) + k);
+        // ---- the rare cases, one element at a time.  Only a vector with a label outside [0, 2^32) reads its labels again
+        //      (a dependent global load here stalled 40 % of the warp-phases when every out-of-window value took it) ----
+        const long long g64 = hv == 0u ? (long long)g : LabelVec<LT>::one(p.labels, (v << 2) + k);
         if ((unsigned long long)g64 >= (unsigned long long)p.size) bad = 1;
         else if (!(NANSKIP && x != x)) {
           const bool slotted = (unsigned long long)g64 < (unsigned long long)cov_c;
           const bool inwin = ab - lo_bits < span_bits;
-          if ((!slotted || !inwin) && ab != 0u) atomicAdd(p.t.t0f + g64, (double)x);   // exact f64 bypass
+          if ((!slotted || !inwin) && ab != 0u) red_add_f64_hint(p.t.t0f + g64, (double)x, l2_evict_last_policy());   // exact f64 bypass
           if (HAS_CNT) {
             if (!slotted) global_count(g64);
             else if (!inwin) { fast = true; q = 0; }            // the count still travels to the owner
@@ -280,21 +290,40 @@ __global__ void __launch_bounds__(TEAM_THREADS, 1) k_team(const TeamParams p) {
           if (slotted && inwin) fast = true;                   // only this vector's OTHER labels were odd
         }
       }
-      const unsigned rel = (p.dbg & 1) ? 0u : ((g - me) & (C - 1));   // 0: mine, j + 1: peer j
-      if (fast && rel == 0u) apply(li, q);
+      q4[k] = q;
+      rel4[k] = (g - me) & (C - 1);                            // 0: mine, j + 1: peer j
+      fastm |= fast ? (1u << k) : 0u;
+    }
+    // ---- step 2: records for the peers (no dependence on my own table) ----
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
 #pragma unroll
       for (int j = 0; j < P; ++j) {
-        const bool go = fast && rel == (unsigned)(j + 1);
+        const bool go = ((fastm >> k) & 1u) && rel4[k] == (unsigned)(j + 1);
         const unsigned m = __ballot_sync(0xffffffffu, go);
         if (go) {
           const unsigned slot = 1u + sent[j] + __popc(m & lt_mask);
-          if (slot < capm) dsm::st_async_rec(dst[j] + slot * 8u, (unsigned)q, li, dbar[j]);
+          if (slot < capm) dsm::st_async_rec(dst[j] + slot * 8u, (unsigned)q4[k], glo[k] >> LOGC, dbar[j]);
           else {                                               // buffer full: the slow exact way
-            if (q != 0) atomicAdd(p.t.t0f + g, (double)x);
-            if (HAS_CNT) global_count((long long)g);
+            if (q4[k] != 0) atomicAdd(p.t.t0f + glo[k], (double)__uint_as_float(xb[k]));
+            if (HAS_CNT) global_count((long long)glo[k]);
           }
         }
         sent[j] += __popc(m);
+      }
+    }
+    // ---- step 3: my own elements: all ATOMS first, then the carry checks ----
+    unsigned old4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      old4[k] = 0u;
+      if (((fastm >> k) & 1u) && rel4[k] == 0u && (!HAS_CNT || q4[k] != 0)) old4[k] = apply_issue(glo[k] >> LOGC, q4[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (((fastm >> k) & 1u) && rel4[k] == 0u) {
+        if (!HAS_CNT || q4[k] != 0) apply_check(glo[k] >> LOGC, q4[k], old4[k]);
+        if (HAS_CNT) count_one(glo[k] >> LOGC);
       }
     }
     // announce the phase: header {count} + one arrival per peer

@@ -315,6 +315,22 @@ int agc_apply_carry(int32_t op, const void* labels, int32_t label_dtype, int64_t
   return 0;
 }
 
+int agc_ordered_accumulate(const agc_request_t* r, const int64_t* order, const int64_t* offsets, void* stream) {
+  if (check_request(r)) return -1;
+  if (!(r->op == AGC_OP_SUM || r->op == AGC_OP_SUMSQ || r->op == AGC_OP_MEAN || r->op == AGC_OP_VAR || r->op == AGC_OP_PROD))
+    return fail(-20, "deterministic mode covers sum / sumofsquares / mean / var / std / prod");
+  if (r->a_dtype != AGC_DT_F32 && r->a_dtype != AGC_DT_F64) return fail(-20, "deterministic mode: integer inputs are order-independent already; values must be float32 / float64");
+  if (!r->a || !order || !offsets) return fail(-6, "agc_ordered_accumulate: null pointer");
+  if (r->workspace_bytes < reduce_layout(r->size).total) return fail(-8, "workspace too small");
+  if (r->size <= 0) return 0;
+  agc::OrderedParams p;
+  p.a = r->a; p.a_dtype = r->a_dtype; p.order = (const long long*)order; p.offsets = (const long long*)offsets; p.size = r->size;
+  p.t = tables_at(r->workspace, reduce_layout(r->size)); p.op = r->op; p.flags = r->flags;
+  AGC_COUNT_LAUNCH(1), agc::k_ordered_accumulate<<<grid_for(r->size * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(p);
+  AGC_CUDA_OK("ordered_accumulate");
+  return 0;
+}
+
 int agc_owner_pack(const agc_request_t* r, int64_t* carrier, int32_t unpack, void* stream) {
   if (check_request(r)) return -1;
   if (r->op != AGC_OP_FIRST && r->op != AGC_OP_LAST) return fail(-2, "agc_owner_pack: first / last only");

@@ -196,9 +196,21 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
             if rc:
                 raise RuntimeError(f"agc_aggregate failed ({rc}): {_abi.last_error()}")
 
-        run(base_flags | _abi.F_ACC_ONLY)
-        req.flags = base_flags
-        _merge_packed(lib, req, ws, status, group, device, stream)
+        ordered = c.deterministic and c.base in ac._ORDERED_OPS and vals is not None and np.issubdtype(c.a_dtype, np.floating)
+        if ordered:
+            # fixed-order mode: every rank adds its own elements in element order, the per-rank tables are folded in RANK order
+            # (all-gather + agc_rank_fold) instead of an all-reduce whose association order is the library's business
+            if c.base in ("var", "std"):
+                raise NotImplementedError("deterministic var / std over shards is not built (single GPU: deterministic=True works)")
+            order_t, offsets_t = ac._group_order(c)
+            req.flags = base_flags | _abi.F_ACC_ONLY
+            if lib.agc_ordered_accumulate(C.byref(req), order_t.data_ptr(), offsets_t.data_ptr(), stream):
+                raise RuntimeError(_abi.last_error())
+            _merge_in_rank_order(lib, req, ws, group, device, stream)
+        else:
+            run(base_flags | _abi.F_ACC_ONLY)
+            req.flags = base_flags
+            _merge_packed(lib, req, ws, status, group, device, stream)
         if c.base in ("var", "std", "argmax", "argmin"):
             run(base_flags | _abi.F_ACC_ONLY | _abi.F_PASS2 | _abi.F_NO_INIT)
             req.flags = base_flags | _abi.F_PASS2
@@ -214,10 +226,30 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
             st = status.cpu()                                    # the only host synchronisation of the call
             if int(st[_abi.ST_BADLABEL]):
                 raise ValueError("group_idx contains negative indices or indices too large for size")
-        ac._LAST["regime"] = int(status[_abi.ST_REGIME].item()) if check else ac._LAST["regime"]
+            ac._LAST["regime"] = int(st[_abi.ST_REGIME])
     if c.out_dtype != compute_out:
         out = ac._Dev(out.t.to(getattr(torch, c.out_dtype.name)), c.out_dtype)
     return ac._finish_shape_torch(c, ac._as_user_tensor(out))
+
+
+def _merge_in_rank_order(lib, req, ws, group, device, stream):
+    """Deterministic merge of the (sum | product, count, touched) tables: all-gather, then fold rank 0, 1, 2, ... in that
+    order on every rank (agc_rank_fold with rank = world) -- the association order of the floating additions is fixed."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    size = req.size
+    s8 = (size * 8 + 255) // 256 * 256                          # table carve-up of the reduction workspace (aggcuda.cu reduce_layout)
+    t0 = ws[0:size * 8].view(torch.float64)
+    t1 = ws[s8:s8 + size * 8].view(torch.int64)
+    b1 = ws[3 * s8 + (size + 255) // 256 * 256:3 * s8 + (size + 255) // 256 * 256 + size]
+    red = 3 if req.op == _abi.OP["prod"] else 0
+    for tab, code, rcode in ((t0, _abi.DT["float64"], red), (t1, _abi.DT["int64"], 0)):
+        gathered = torch.empty((world, size), dtype=tab.dtype, device=device)
+        dist.all_gather_into_tensor(gathered, tab, group=group)
+        if lib.agc_rank_fold(gathered.data_ptr(), world, size, code, rcode, tab.data_ptr(), stream):
+            raise RuntimeError(_abi.last_error())
+    dist.all_reduce(b1, op=dist.ReduceOp.MAX, group=group)      # 0/1 flags: order cannot matter
 
 
 def _merge_owner_values(lib, req, size, group, device, stream):

@@ -106,19 +106,36 @@ def test_aggregate_multi_matches_single_calls(adtype, groups, fill):
     a = rng.standard_normal(n).astype(adtype)
     a[rng.random(n) < 0.05] = np.nan
     funcs = ["sum", "mean", "len", "var", "std", "min", "max", "nansum", "nanmean", "nanvar", "nanlen", "nanmin", "nanmax", "first"]
-    res = ac.aggregate_multi(g, a, funcs, size=groups, fill_value=fill, ddof=1)
-    assert list(res) == funcs
+    # a member the reference would reject (len with fill_value=nan: ValueError) makes the fused call raise like the single call
+    singles, rejected = {}, []
     for f in funcs:
         kw = {"ddof": 1} if f.replace("nan", "") in ("var", "std") else {}
         try:
-            one = aggregate(g, a, f, size=groups, fill_value=fill, **kw)
-        except ValueError:                                    # e.g. len with fill nan: the fused call raised too or fell back
-            continue
+            singles[f] = aggregate(g, a, f, size=groups, fill_value=fill, **kw)
+        except ValueError:
+            rejected.append(f)
+    if rejected:
+        with pytest.raises(ValueError):
+            ac.aggregate_multi(g, a, funcs, size=groups, fill_value=fill, ddof=1)
+        funcs = [f for f in funcs if f not in rejected]
+    res = ac.aggregate_multi(g, a, funcs, size=groups, fill_value=fill, ddof=1)
+    assert list(res) == funcs
+    for f in funcs:
+        one = singles[f]
         assert res[f].dtype == one.dtype and res[f].shape == one.shape, f
         if f in ("len", "nanlen", "min", "max", "nanmin", "nanmax", "first"):
             np.testing.assert_array_equal(res[f], one, err_msg=f)
         else:
-            np.testing.assert_allclose(res[f], one, rtol=1e-5 if adtype == np.float32 else 1e-12, atol=1e-30, err_msg=f)
+            # two runs add the same f64 terms in different orders: per-group floor = 1e-12 of the group's own sum of |a|
+            x = np.nan_to_num(a.astype(np.float64), nan=0.0)
+            cnt = np.maximum(np.bincount(g, minlength=groups), 1).astype(np.float64)
+            s1, s2 = np.bincount(g, weights=np.abs(x), minlength=groups), np.bincount(g, weights=x * x, minlength=groups)
+            base = f.replace("nan", "")
+            floor = {"sum": 1e-12 * s1, "mean": 1e-12 * s1 / cnt, "var": 1e-9 * s2 / cnt, "std": np.sqrt(1e-9 * s2 / cnt)}[base]
+            rtol = (2e-5 if base in ("var", "std") else 1e-5) if adtype == np.float32 else 1e-12
+            r64, o64 = res[f].astype(np.float64), one.astype(np.float64)
+            ok = (np.isnan(r64) & np.isnan(o64)) | (np.abs(r64 - o64) <= rtol * np.abs(o64) + floor + 1e-300)
+            assert ok.all(), (f, np.flatnonzero(~ok)[:5], r64[~ok][:5], o64[~ok][:5])
 
 
 def test_aggregate_multi_against_oracle_and_launch_savings():
@@ -198,3 +215,54 @@ def test_duck_arrays():
     g, a = np.array([0, 1, 1, 3]), np.array([1.0, 2.0, 3.0, 4.0])
     assert ac.is_duck_array(Duck(a)) and ac.is_duck_array(a) and ac.is_duck_array(torch.zeros(2)) and not ac.is_duck_array([1, 2])
     np.testing.assert_array_equal(aggregate(Duck(g), Duck(a)), [1.0, 5.0, 0.0, 4.0])
+
+
+@pytest.mark.parametrize("adtype", [np.float32, np.float64])
+@pytest.mark.parametrize("groups", [50, 30000, 400000])
+def test_deterministic_mode_same_bits_every_time(adtype, groups):
+    """deterministic=True: floating sums / means / variances / products add every group's elements in a fixed order (device
+    sort by group, one warp per group).  Same input, same bits -- whatever the kernel tuning -- and still the reference's answer."""
+    import torch
+    rng = np.random.default_rng(groups)
+    n = (1 << 20) + 13
+    g = rng.integers(0, groups, n)
+    a = (rng.standard_normal(n) * np.exp2(rng.integers(-20, 20, n))).astype(adtype)       # wide range, both signs: order matters
+    a[rng.random(n) < 0.02] = np.nan
+    tg, ta = torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda()
+    for func, kw in (("nansum", {}), ("nanmean", {}), ("nanvar", dict(ddof=1)), ("nanstd", {}), ("sum", {}), ("sumofsquares", {}), ("nanprod", {})):
+        vals = ta if func != "nanprod" else (1 + ta * 0).where(torch.isnan(ta), 1 + ta.sign() * 1e-3)
+        runs = []
+        for fast in (True, False, True):
+            runs.append(aggregate(tg, vals, func, size=groups, deterministic=True, fast=fast, **kw))
+        assert torch.equal(runs[0].view(torch.int32 if adtype == np.float32 else torch.int64),
+                           runs[1].view(torch.int32 if adtype == np.float32 else torch.int64)), func
+        assert torch.equal(runs[0].view(torch.int32 if adtype == np.float32 else torch.int64),
+                           runs[2].view(torch.int32 if adtype == np.float32 else torch.int64)), func
+        if func == "nanprod":
+            continue
+        with np.errstate(all="ignore"):
+            ref = oracle.aggregate(g, a, func=func, size=groups, **kw)
+        got = runs[0].cpu().numpy()
+        assert got.dtype == ref.dtype
+        x = np.nan_to_num(a.astype(np.float64), nan=0.0)
+        cnt = np.maximum(np.bincount(g, minlength=groups), 1).astype(np.float64)
+        s1, s2 = np.bincount(g, weights=np.abs(x), minlength=groups), np.bincount(g, weights=x * x, minlength=groups)
+        base = func.replace("nan", "")
+        floor = {"sum": 1e-12 * s1, "mean": 1e-12 * s1 / cnt, "var": 1e-9 * s2 / cnt, "std": np.sqrt(1e-9 * s2 / cnt), "sumofsquares": 1e-12 * s2}[base]
+        rtol = 1e-5 if adtype == np.float32 else 1e-12
+        ok = (np.isnan(got) & np.isnan(ref)) | (np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= rtol * np.abs(ref) + floor + 1e-300)
+        assert ok.all(), (func, np.flatnonzero(~ok)[:5])
+
+
+def test_deterministic_mode_forms_and_fill():
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((50, 2000)).astype(np.float32)
+    g = rng.integers(0, 30, 2000)
+    for func in ("sum", "mean", "std"):
+        got = aggregate(g, a, func, size=31, axis=1, fill_value=-5, deterministic=True)
+        ref = oracle.aggregate(g, a, func=func, size=31, axis=1, fill_value=-5)
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    gi = rng.integers(0, 9, (2, 5000))
+    ai = rng.integers(-5, 5, 5000)
+    np.testing.assert_array_equal(aggregate(gi, ai, "sum", size=(9, 9), deterministic=True), oracle.aggregate(gi, ai, func="sum", size=(9, 9)))

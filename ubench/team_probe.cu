@@ -196,7 +196,7 @@ int main(int argc, char** argv) {
   memset(&p, 0, sizeof(p));
   p.labels = labels; p.a = a; p.n = n; p.size = G;
   p.t.t0f = s_out; p.t.t0i = (long long*)s_out; p.t.t1 = c_out; p.t.b1 = b1; p.status = status;
-  p.flags = 0; p.want_cnt = 1; p.want_b1 = 0; p.cov = cov; p.cap = cap; p.choose = nullptr; p.want = 0; p.dbg = dbg;
+  p.flags = 0; p.want_cnt = 1; p.want_b1 = 0; p.cov = cov; p.cap = cap; p.choose = nullptr; p.want = 0; (void)dbg;
 
   int ncl = dispatch(C, mode, xport, p, smem, mc);
   if (ncl < 0) { printf("{\"error\": \"launch rc %d\", \"smem\": %zu}\n", ncl, smem); return 1; }
