@@ -36,56 +36,67 @@ constexpr int PROBE_SAMPLES = 32768;                // at n >= 2^23; fewer for s
 // the elements adds >= 33: beyond that share its uncovered elements serialise on ONE L2 address (measured 1.5 ns per
 // RED: a 0.5 % group doubles the partial-table kernel's time, 1.5 % makes it 5x) and the hot-key cache wins.
 constexpr int PROBE_SKEW_COUNT = 40;
+// The probe is spread over samples / 1024 CTAs (one sample per thread: a single dependent round trip to memory instead of
+// the 32 a lone CTA needed -- 77 us per call in round 1, 13 % of a 2^27-element step).  Every CTA adds its bucket and
+// exponent histograms to a scratch area in the caller's workspace; the last one to finish (a ticket counter) reads the
+// totals and writes status[4..7] (the dispatcher zeroes the scratch area before every probe).
+constexpr int PROBE_SCRATCH_WORDS = 4096 + 256 + 8;  // bucket histogram, exponent histogram, {adjacent-equal count, ticket}
 template <class LT>
-__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int samples, int thresh, const float* a = nullptr) {
+__global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long long n, int* status, int samples, int thresh,
+                                                     unsigned* scratch, const float* a = nullptr) {
   __shared__ unsigned cnt[4096];
-  __shared__ unsigned s_max, s_adj, s_emax, s_low;
+  __shared__ unsigned ecnt[256];
+  __shared__ unsigned s_adj, s_last;
   for (int i = threadIdx.x; i < 4096; i += 1024) cnt[i] = 0;
-  if (threadIdx.x == 0) { s_max = 0; s_adj = 0; s_emax = 0; s_low = 0; }
+  if (threadIdx.x < 256) ecnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_adj = 0; s_last = 0; }
   __syncthreads();
   const long long stride = n / samples;                // >= 2 (callers guarantee n >= 65536 and samples <= n / 16)
-  unsigned adj = 0, emax = 0;
-#pragma unroll 8
-  for (int j = 0; j < samples / 1024; ++j) {
-    const long long i = ((long long)j * 1024 + threadIdx.x) * stride;
-    const long long g = LabelVec<LT>::one(labels, i), gn = LabelVec<LT>::one(labels, i + 1);
-    atomicAdd(&cnt[((unsigned)g * 0x9E3779B1u) >> 20], 1u);
-    adj += g == gn;
-    if (a) {                                           // biased exponents of the sampled values (zero / inf / NaN aside)
-      const unsigned e = (__float_as_uint(a[i]) >> 23) & 0xffu;
-      if (e != 255u) emax = max(emax, e);
-    }
-  }
-  if (a) {                                              // second look at the same samples: how many lie > 14 binades below the largest
-    emax = __reduce_max_sync(0xffffffffu, emax);
-    if ((threadIdx.x & 31) == 0) atomicMax(&s_emax, emax);
-    __syncthreads();
-    const unsigned floor_e = s_emax > 14u ? s_emax - 14u : 0u;
-    unsigned low = 0;
-#pragma unroll 8
-    for (int j = 0; j < samples / 1024; ++j) {
-      const unsigned bits = __float_as_uint(a[((long long)j * 1024 + threadIdx.x) * stride]) & 0x7fffffffu;
-      low += bits != 0u && (bits >> 23) < floor_e;
-    }
-    low = __reduce_add_sync(0xffffffffu, low);
-    if ((threadIdx.x & 31) == 0 && low) atomicAdd(&s_low, low);
+  const long long i = ((long long)blockIdx.x * 1024 + threadIdx.x) * stride;
+  const long long g = LabelVec<LT>::one(labels, i), gn = LabelVec<LT>::one(labels, i + 1);
+  atomicAdd(&cnt[((unsigned)g * 0x9E3779B1u) >> 20], 1u);
+  unsigned adj = g == gn;
+  if (a) {                                              // biased exponent of the sampled value (zero / inf / NaN aside)
+    const unsigned bits = __float_as_uint(a[i]) & 0x7fffffffu;
+    const unsigned e = bits >> 23;
+    if (bits != 0u && e != 255u) atomicAdd(&ecnt[e], 1u);
   }
   adj = __reduce_add_sync(0xffffffffu, adj);
   if ((threadIdx.x & 31) == 0 && adj) atomicAdd(&s_adj, adj);
   __syncthreads();
+  unsigned* g_cnt = scratch; unsigned* g_ecnt = scratch + 4096; unsigned* g_misc = scratch + 4096 + 256;
+  for (int k = threadIdx.x; k < 4096; k += 1024) if (cnt[k]) atomicAdd(g_cnt + k, cnt[k]);
+  if (threadIdx.x < 256 && ecnt[threadIdx.x]) atomicAdd(g_ecnt + threadIdx.x, ecnt[threadIdx.x]);
+  if (threadIdx.x == 0 && s_adj) atomicAdd(g_misc, s_adj);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(g_misc + 1, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- the last CTA: totals -> decision, scratch back to zero ----
+  __threadfence();
+  __shared__ unsigned s_max, s_emax, s_low;
+  if (threadIdx.x == 0) { s_max = 0; s_emax = 0; s_low = 0; }
+  __syncthreads();
   unsigned m = 0;
-  for (int i = threadIdx.x; i < 4096; i += 1024) m = max(m, cnt[i]);
+  for (int k = threadIdx.x; k < 4096; k += 1024) { m = max(m, __ldcg(g_cnt + k)); g_cnt[k] = 0u; }
   m = __reduce_max_sync(0xffffffffu, m);
   if ((threadIdx.x & 31) == 0) atomicMax(&s_max, m);
+  unsigned ec = 0;
+  if (threadIdx.x < 256) { ec = __ldcg(g_ecnt + threadIdx.x); g_ecnt[threadIdx.x] = 0u; if (ec) atomicMax(&s_emax, (unsigned)threadIdx.x); }
+  __syncthreads();
+  if (threadIdx.x < 256 && ec && s_emax > 14u && (unsigned)threadIdx.x < s_emax - 14u) atomicAdd(&s_low, ec);   // > 14 binades below the largest
   __syncthreads();
   if (threadIdx.x == 0) {
+    const unsigned t_adj = __ldcg(g_misc);
+    g_misc[0] = 0u; g_misc[1] = 0u;
     // 2: labels come in runs (sorted / contiguous) -> segmented warp reduce; 1: skewed -> hot-key cache; 0: neither
-    status[4] = s_adj > (unsigned)samples / 2 ? 2 : ((s_max > (unsigned)thresh || s_adj > (unsigned)samples / 8) ? 1 : 0);
+    status[4] = t_adj > (unsigned)samples / 2 ? 2 : ((s_max > (unsigned)thresh || t_adj > (unsigned)samples / 8) ? 1 : 0);
     status[5] = (int)s_max;
-    status[6] = (int)s_adj;
+    status[6] = (int)t_adj;
     // 1: more than 0.1 % of the sampled values lie below the two-word fixed-point window (16 binades, minus a margin)
     // of the largest one: the hot-key cache then gives every slot an f64 side accumulator
-    status[7] = (a && s_low * 1024u > (unsigned)samples) ? 1 : 0;        // more than 0.1 % of the samples
+    status[7] = (a && s_low * 1024u > (unsigned)samples) ? 1 : 0;
   }
 }
 
@@ -182,7 +193,7 @@ inline int try_fast_pass2(const agc_request_t* r, const Tables& t, cudaStream_t 
 }
 
 // returns 1 if it accumulated into the global tables (which it also initialises), 0 to fall back
-inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms) {
+inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t st, int sms, unsigned* probe_scratch) {
   if (r->index.form == AGC_FORM_AXIS) return try_form3_path(r, t, st, sms);
   if (r->index.form != AGC_FORM_FLAT) return 0;
   if (r->index.dtype != AGC_DT_I64 && r->index.dtype != AGC_DT_I32) return 0;
@@ -288,8 +299,9 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     samples = samples < 4096 ? 4096 : (samples > PROBE_SAMPLES ? PROBE_SAMPLES : samples);
     samples &= ~1023ll;
     const int thresh = (int)(12 + samples * (PROBE_SKEW_COUNT - 12) / PROBE_SAMPLES);
-    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
-    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh);
+    cudaMemsetAsync(probe_scratch, 0, (size_t)PROBE_SCRATCH_WORDS * 4, st);       // the workspace is the caller's: nothing in it is zero yet
+    if (i64) k_skew_probe<long long><<<(int)(samples / 1024), 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, probe_scratch);
+    else k_skew_probe<int><<<(int)(samples / 1024), 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, probe_scratch);
     AGC_COUNT_LAUNCH(1);
     p.choose = r->status + 4; p.want = 0;
     // labels the probe calls uniform: groups past the filter table always pass (one RED each; no group holds more than
@@ -331,8 +343,9 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     samples &= ~1023ll;
     const int thresh = (int)(12 + samples * (PROBE_SKEW_COUNT - 12) / PROBE_SAMPLES);       // 40 at 32 Ki samples (0.1 % share), 15 at 4 Ki (0.35 %)
     const float* pa = need_a ? (const float*)r->a : nullptr;
-    if (i64) k_skew_probe<long long><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, pa);
-    else k_skew_probe<int><<<1, 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, pa);
+    cudaMemsetAsync(probe_scratch, 0, (size_t)PROBE_SCRATCH_WORDS * 4, st);
+    if (i64) k_skew_probe<long long><<<(int)(samples / 1024), 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, probe_scratch, pa);
+    else k_skew_probe<int><<<(int)(samples / 1024), 1024, 0, st>>>(r->index.labels, r->n, r->status, (int)samples, thresh, probe_scratch, pa);
     AGC_COUNT_LAUNCH(1);
   }
   if (uniform_kernel == 3) {

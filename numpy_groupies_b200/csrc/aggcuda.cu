@@ -48,7 +48,7 @@ struct Layout { int64_t t0, t1, t2, b0, b1, extra, total; };
 Layout reduce_layout(int64_t size) {
   Layout L; int64_t s8 = align_up(size * 8, 256), s1 = align_up(size, 256);
   L.t0 = 0; L.t1 = s8; L.t2 = 2 * s8; L.b0 = 3 * s8; L.b1 = 3 * s8 + s1; L.extra = 3 * s8 + 2 * s1;
-  L.total = L.extra;
+  L.total = L.extra + align_up((int64_t)agc::PROBE_SCRATCH_WORDS * 4, 256);      // extra: the label probe's histograms
   return L;
 }
 agc::Tables tables_at(void* ws, const Layout& L) {
@@ -183,7 +183,7 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
       if (!(r->flags & AGC_F_NO_FAST) && !(r->flags & AGC_F_NO_INIT) && r->size > 0 && r->n > 0) {
         // specialised shared-memory kernels (they initialise + write the same global tables)
         prof_begin(st);
-        int frc = agc::try_fast_path(r, t, st, sm_count());
+        int frc = agc::try_fast_path(r, t, st, sm_count(), (unsigned*)((char*)r->workspace + L.extra));
         if (frc < 0) return fail(frc, "fast path launch failed");
         done = frc > 0;
         if (done) prof_end(st);

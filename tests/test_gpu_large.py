@@ -678,7 +678,7 @@ def test_second_launch_chunk_at_n_2p30():
         before = lib.agc_launch_count()
         got = aggregate(lab, a, func=func, size=groups)
         launches = lib.agc_launch_count() - before
-        if func in ("sum", "mean", "nansum"):
+        if func in ("sum", "mean"):                         # one CTA per SM (table > 97 KB): 148 x 2^22 elements per launch < 2^30
             assert launches >= 4, (func, launches)          # init + two (or more) accumulate launches + finalise
         sums = torch.zeros(groups, dtype=torch.float64, device=dev)
         cnt = torch.zeros(groups, dtype=torch.int64, device=dev)
