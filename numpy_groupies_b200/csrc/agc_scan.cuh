@@ -499,10 +499,17 @@ __device__ __forceinline__ A scan_from_raw(const ScanParams& p, unsigned long lo
 // elements 8t .. 8t+7) as the thread-local scan needs.  The 2 KB staging buffer per warp is XOR-swizzled
 // (chunk c lives at c ^ ((c >> 2) & 7)) so that both the striped and the blocked side are bank-conflict free.
 // Per-thread 64-byte loads reach the same DRAM bytes but cost 4x the L1 wavefronts (ncu: L1TEX 98 % busy).
-__device__ __forceinline__ void warp_load_blocked8(const void* src_warp, int4* wbuf, int lane, unsigned long long (&out)[SG_ITEMS]) {
+// step 1: the coalesced global loads of one 2 KB warp slice (lane l -> chunk k * 32 + l), nothing else -- callers issue the
+// loads of labels AND values before they touch either (one memory round trip per tile instead of two)
+__device__ __forceinline__ void warp_fetch8(const void* src_warp, int lane, int4 (&raw)[4]) {
   const int4* q = (const int4*)src_warp;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { const int c = k * 32 + lane; wbuf[c ^ ((c >> 2) & 7)] = q[c]; }
+  for (int k = 0; k < 4; ++k) raw[k] = q[k * 32 + lane];
+}
+// step 2: through the XOR-swizzled staging buffer into BLOCKED registers (thread t holds elements 8t .. 8t+7)
+__device__ __forceinline__ void warp_transpose8(const int4 (&raw)[4], int4* wbuf, int lane, unsigned long long (&out)[SG_ITEMS]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int c = k * 32 + lane; wbuf[c ^ ((c >> 2) & 7)] = raw[k]; }
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -512,6 +519,11 @@ __device__ __forceinline__ void warp_load_blocked8(const void* src_warp, int4* w
     out[2 * j + 1] = ((unsigned long long)(unsigned)v.z) | ((unsigned long long)(unsigned)v.w << 32);
   }
   __syncwarp();
+}
+__device__ __forceinline__ void warp_load_blocked8(const void* src_warp, int4* wbuf, int lane, unsigned long long (&out)[SG_ITEMS]) {
+  int4 raw[4];
+  warp_fetch8(src_warp, lane, raw);
+  warp_transpose8(raw, wbuf, lane, out);
 }
 __device__ __forceinline__ void warp_store_blocked8(void* dst_warp, int4* wbuf, int lane, const unsigned long long (&in)[SG_ITEMS]) {
 #pragma unroll
@@ -640,9 +652,13 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
   const bool wfull = wbase + 32 * SG_ITEMS <= p.n;          // warp-uniform
   const bool tr_lab = wfull && sizeof(LT) == 8;
   const bool tr_val = wfull && dtype_bytes(p.a_dtype) == 8 && !((uintptr_t)p.a & 15);
+  // both transposed streams: all global loads first, then the two trips through the staging buffer
+  int4 raw_lab[4], raw_val[4];
+  if (tr_lab) warp_fetch8((const long long*)p.labels + wbase, lane, raw_lab);
+  if (tr_val) warp_fetch8((const unsigned long long*)p.a + wbase, lane, raw_val);
   if (tr_lab) {
     unsigned long long gl[SG_ITEMS];
-    warp_load_blocked8((const long long*)p.labels + wbase, s_stage[wrp], lane, gl);
+    warp_transpose8(raw_lab, s_stage[wrp], lane, gl);
 #pragma unroll
     for (int k = 0; k < SG_ITEMS; ++k) g[k] = (long long)gl[k];
   } else load_labels8<LT>(p.labels, base, p.n, g);
@@ -653,7 +669,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
   bool tf = false; A tx = A(0); bool any = false, uns = false, bad = false;
   const bool vec = base + SG_ITEMS <= p.n && raw8_ok(p.a_dtype) && !((uintptr_t)p.a & 15);
   unsigned long long raw[SG_ITEMS];
-  if (tr_val) warp_load_blocked8((const unsigned long long*)p.a + wbase, s_stage[wrp], lane, raw);
+  if (tr_val) warp_transpose8(raw_val, s_stage[wrp], lane, raw);
   else if (vec) load_raw8(p.a, p.a_dtype, base, raw);
 #pragma unroll
   for (int k = 0; k < SG_ITEMS; ++k) {

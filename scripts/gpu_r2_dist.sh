@@ -6,7 +6,7 @@ mkdir -p gpurun_out/r2dist
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py > gpurun_out/r2dist/check_${N}.log 2>&1
 tail -6 gpurun_out/r2dist/check_${N}.log | cut -c1-300
 for sc in weak strong; do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --scaling $sc --no-sweep > gpurun_out/r2dist/bench_${N}_${sc}.json 2> gpurun_out/r2dist/bench_${N}_${sc}.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --scaling $sc $( [ "$sc" = "strong" ] && echo --no-sweep ) > gpurun_out/r2dist/bench_${N}_${sc}.json 2> gpurun_out/r2dist/bench_${N}_${sc}.err
   tail -2 gpurun_out/r2dist/bench_${N}_${sc}.err | cut -c1-300
   python - <<PY
 import json
