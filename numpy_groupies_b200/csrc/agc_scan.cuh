@@ -564,10 +564,10 @@ template <> __device__ __forceinline__ long long scan_unbits<long long>(unsigned
 template <> __device__ __forceinline__ double scan_unbits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
 
 // called by the 32 threads of warp 0; returns the carry into tile t (t > 0): the running value at the end of tile t - 1.
-// A round fetches LB_W windows of 32 descriptors at once (lane l: tiles t-1-l, t-33-l, ...): the chain of published
-// prefixes then advances 32 * LB_W tiles per L2 round trip.  With one window per round it advanced 32 tiles per ~0.7 us
-// while a 6.5 TB/s stream retires ~130 tiles of 2048 elements per us -- the scan ran at the pace of its look-back.
-constexpr int LB_W = 4;
+// A round fetches LB_W windows of 32 descriptors at once (lane l: tiles t-1-l, t-33-l, ...).  Measured at N = 2^28
+// (cumsum, sorted int64 labels): LB_W = 1 2.24 ms, LB_W = 4 2.34 ms -- a wider round waits for more predecessors to
+// publish and gains nothing, the look-back is bound by WHEN the aggregates appear, not by how many it can read at once.
+constexpr int LB_W = 1;
 template <class A, int OP>
 __device__ __forceinline__ A chain_lookback(const unsigned long long* desc, int t, int lane) {
   A acc = A(0); bool have = false;
@@ -1047,7 +1047,11 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
   if (scan_chain_enabled() && !(p.flags & AGC_F_DETERMINISTIC)) {          // one pass, 24 B/element: tile descriptors + warp-parallel look-back
     cudaMemsetAsync(ws + L.desc, 0, (size_t)ntiles * 16, st);
     int nfull = 0;
-    if (sizeof(LT) == 8 && dtype_bytes(p.a_dtype) == 8 && !((uintptr_t)p.a & 15)) {
+    // (the persistent variant with the next tile's loads in flight measured SLOWER -- 3.08 against 2.24 ms for cumsum at
+    //  N = 2^28, profiles/r02f_scan_*.jsonl: two CTAs of 128 registers per SM leave nothing to run while a CTA waits for its
+    //  look-back -- and stays behind AGC_SCAN_PERSIST=1 as a record of the experiment)
+    static const bool persist = getenv("AGC_SCAN_PERSIST") && atoi(getenv("AGC_SCAN_PERSIST")) == 1;
+    if (persist && sizeof(LT) == 8 && dtype_bytes(p.a_dtype) == 8 && !((uintptr_t)p.a & 15)) {
       // full tiles of the all-64-bit case: persistent kernel, next tile's loads in flight (2 CTAs per SM)
       nfull = (int)(p.n / SG_TILE);
       if (nfull > 0) {
