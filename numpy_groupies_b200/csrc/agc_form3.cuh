@@ -30,6 +30,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
   __shared__ int s_item;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
   constexpr bool IS_SUM = MODE == FM_SUM || MODE == FM_SUMCNT;
+  // Fixed-point grid of THIS kernel: 31 fraction bits, so |q| < 2^31 and the high word only moves on a carry out of the low
+  // one (~1.25 ATOMS per element instead of 2: the kernel is bound by the shared-memory atomic rate).  The price is an
+  // 7-binade exact window; what falls below it (0.8 % of rand() values) takes the f64 RED -- harmless HERE because the
+  // global table has rows x G entries (the same trick lost on Form 1 with 100 groups, where those REDs pile on 100
+  // addresses: agc_fast.cuh keeps 40 bits there).
+  constexpr int FXF3 = 31, FXW3 = FXF3 - 24;
   const int G = (int)p.G, T = RB * G;
   unsigned* w0 = sw; unsigned* w1 = sw + T; unsigned* w2 = sw + 2 * T;
   const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
@@ -74,11 +80,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
       int eb = (int)(s_maxbits >> 23);
       if (eb == 0) eb = 127;
       eb += 1;
-      int lo_e = eb - FX_WINDOW; if (lo_e < 1) lo_e = 1;
+      int lo_e = eb - FXW3; if (lo_e < 1) lo_e = 1;
       lo_bits = (unsigned)lo_e << 23;
       span_bits = (unsigned)(eb - lo_e) << 23;
-      scale = __longlong_as_double((long long)(1023 + FX_F - (eb - 127)) << 52);
-      inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
+      scale = __longlong_as_double((long long)(1023 + FXF3 - (eb - 127)) << 52);
+      inv_scale = __longlong_as_double((long long)(1023 - FXF3 + (eb - 127)) << 52);
     }
 
     auto update = [&](int gi, long long gflat, float x) {

@@ -300,6 +300,7 @@ struct ScanParams {
   int a_u64;
   const void* labels; long long size; int* status; int* unsorted_w;   // direct (sorted flat labels) path
   int only_if_unsorted;                               // keys path: no-op when the direct path already ran
+  int lb_sleep;                                       // chained scan: nanoseconds a look-back lane sleeps before it polls an unpublished descriptor again
   int tile0;                                          // direct scan: tile of block 0 (the persistent chained kernel took the tiles before it)
   void* gath;                                         // keys path: scan inputs in sorted order (PHASE 0 gathers them once)
 };
@@ -569,7 +570,7 @@ template <> __device__ __forceinline__ double scan_unbits<double>(unsigned long 
 // publish and gains nothing, the look-back is bound by WHEN the aggregates appear, not by how many it can read at once.
 constexpr int LB_W = 1;
 template <class A, int OP>
-__device__ __forceinline__ A chain_lookback(const unsigned long long* desc, int t, int lane) {
+__device__ __forceinline__ A chain_lookback(const unsigned long long* desc, int t, int lane, unsigned sleep_ns = 0) {
   A acc = A(0); bool have = false;
   int look = t - 1 - lane;
   for (;;) {
@@ -584,7 +585,10 @@ __device__ __forceinline__ A chain_lookback(const unsigned long long* desc, int 
     for (int w = 0; w < LB_W; ++w) {
       if (done) break;
       const int lk = look - 32 * w;
-      while (lk >= 0 && (m[w] & 3ull) == 0ull) desc_load(desc + 2 * (long long)lk, m[w], xb[w]);   // not published yet: wait for it
+      while (lk >= 0 && (m[w] & 3ull) == 0ull) {               // not published yet: wait for it (backing off keeps the pollers
+        if (sleep_ns) __nanosleep(sleep_ns);                   // from fighting the publisher for the descriptor's L2 line)
+        desc_load(desc + 2 * (long long)lk, m[w], xb[w]);
+      }
       const bool term = (m[w] & 3ull) == 2ull || (m[w] & 0x100ull) != 0ull;
       const unsigned tb = __ballot_sync(0xffffffffu, term);
       const int first = tb ? __ffs((int)tb) - 1 : 32;          // nearest terminator in this window
@@ -707,7 +711,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
       if (lane == 0) desc_store(desc + 2 * (long long)t, (t == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
       A c = A(0);
       if (t > 0) {
-        c = chain_lookback<A, OP>(desc, t, lane);
+        c = chain_lookback<A, OP>(desc, t, lane, (unsigned)p.lb_sleep);
         if (lane == 0) desc_store(desc + 2 * (long long)t, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
       }
       if (lane == 0) s_carry = scan_bits<A>(c);
@@ -825,7 +829,7 @@ __global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_chain8(const ScanPar
       if (lane == 0) desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
       A c = A(0);
       if (tile > 0) {
-        c = chain_lookback<A, OP>(desc, tile, lane);
+        c = chain_lookback<A, OP>(desc, tile, lane, (unsigned)p.lb_sleep);
         if (lane == 0) desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
       }
       if (lane == 0) s_carry = scan_bits<A>(c);
@@ -1102,6 +1106,7 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
   p.fill_f = r->fill_f64; p.fill_i = r->fill_i64;
   p.a_float = dtype_is_float(r->a_dtype); p.a_u64 = r->a_dtype == AGC_DT_U64;
   p.labels = r->index.labels; p.size = r->size; p.status = r->status;
+  { static const int lb_sleep = getenv("AGC_LB_SLEEP") ? atoi(getenv("AGC_LB_SLEEP")) : 0; p.lb_sleep = lb_sleep; }
 
   // ---- flat int32/int64 labels: try the direct (already sorted) scan first -------------------------------
   int direct_lt = 0;

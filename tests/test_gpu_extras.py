@@ -266,3 +266,26 @@ def test_deterministic_mode_forms_and_fill():
     gi = rng.integers(0, 9, (2, 5000))
     ai = rng.integers(-5, 5, 5000)
     np.testing.assert_array_equal(aggregate(gi, ai, "sum", size=(9, 9), deterministic=True), oracle.aggregate(gi, ai, func="sum", size=(9, 9)))
+
+
+def test_second_device_in_the_same_process():
+    """Per-device host state (round-1 advisor finding): the dynamic shared-memory attribute, the SM count and the profile
+    events are per device; a process that used cuda:0 must be able to run every large-table kernel on cuda:1."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    rng = np.random.default_rng(3)
+    n = 1 << 21
+    for groups in (100, 30000, 100000):
+        g = rng.integers(0, groups, n)
+        a = rng.random(n, dtype=np.float32)
+        ref = {f: oracle.aggregate(g, a, func=f, size=groups) for f in ("sum", "mean", "max", "len")}
+        for dev in ("cuda:0", "cuda:1", "cuda:0"):
+            tg, ta = torch.from_numpy(g).to(dev), torch.from_numpy(a).to(dev)
+            for f, r in ref.items():
+                got = aggregate(tg, ta, f, size=groups)
+                assert str(got.device) == dev
+                if f in ("max", "len"):
+                    np.testing.assert_array_equal(got.cpu().numpy(), r)
+                else:
+                    np.testing.assert_allclose(got.cpu().numpy(), r, rtol=1e-5)
