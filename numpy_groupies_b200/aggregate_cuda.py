@@ -44,7 +44,7 @@ _LAST = {"regime": 0, "probe": (0, 0, 0)}
 def last_regime():
     """Which accumulate kernel the last checked call used (status[3] of the C ABI): 0 general global-table
     kernel, 10+mode k_fast (mode: 0 sum, 1 sum+count, 2 max, 3 min, 4 len, 5 one-word sum), 16 k_len16, 17 / 18
-    k_maxfilter max / min, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs, 60 k_accumulate_small, 70 / 71 k_team (sums /
+    k_maxfilter max / min, 20+mode k_cache, 40+mode k_form3, 50+mode k_runs, 30 k_fast fused min + max, 60 k_accumulate_small, 70 / 71 k_team (sums /
     sums + counts on a cluster of SMs)."""
     return _LAST["regime"]
 
@@ -881,6 +881,7 @@ def _fused_family(group_idx, a, members, family, size, fill_value, order, axis, 
             st = status.cpu().numpy()
             if st[_abi.ST_BADLABEL]:
                 raise ValueError("group_idx contains negative indices or indices too large for size")
+            _LAST["regime"] = int(st[_abi.ST_REGIME])
     final = {}
     for nm, o in results.items():
         c = calls[nm]

@@ -200,7 +200,8 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   const int op = r->op;
   const bool is_len = op == AGC_OP_LEN;
   const bool nanskip = r->flags & AGC_F_NANSKIP;
-  if (!(op == AGC_OP_SUM || op == AGC_OP_SUMSQ || op == AGC_OP_MEAN || op == AGC_OP_MIN || op == AGC_OP_MAX || is_len || op == AGC_OP_VAR))
+  if (!(op == AGC_OP_SUM || op == AGC_OP_SUMSQ || op == AGC_OP_MEAN || op == AGC_OP_MIN || op == AGC_OP_MAX || is_len || op == AGC_OP_VAR ||
+        op == AGC_OP_MINMAX))
     return 0;
   const bool need_a = !is_len || nanskip;
   if (need_a && (r->a == nullptr || r->a_dtype != AGC_DT_F32)) return 0;
@@ -211,10 +212,13 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
   if (is_len) mode = FM_LEN;
   else if (op == AGC_OP_MAX) mode = FM_MAX;
   else if (op == AGC_OP_MIN) mode = FM_MIN;
+  else if (op == AGC_OP_MINMAX) mode = FM_MINMAX;
   else if (op == AGC_OP_MEAN || op == AGC_OP_VAR || want_b1) mode = FM_SUMCNT;
   else mode = FM_SUM;
-  const int words = mode == FM_SUM ? 2 : (mode == FM_SUMCNT ? 3 : 1);
+  const int words = (mode == FM_SUM || mode == FM_MINMAX) ? 2 : (mode == FM_SUMCNT ? 3 : 1);
   tuning_defaults();
+  // fused min + max: two key words per group while the whole table fits one SM; larger tables run on the general kernel
+  if (mode == FM_MINMAX && (size_t)r->size * 8 > smem_cap1()) return 0;
   const size_t cap2 = smem_cap2(), cap1 = smem_cap1();
   const size_t table = (size_t)r->size * words * 4;
   const bool direct = table <= cap1;          // whole table privatised per CTA
@@ -240,6 +244,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
 #define AGC_FAST_ALL(LAUNCHER, ...)                                                                              \
   AGC_FAST_LAUNCH(LAUNCHER, FM_SUM, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_SUMCNT, __VA_ARGS__)                 \
   AGC_FAST_LAUNCH(LAUNCHER, FM_MAX, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_MIN, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_LEN, __VA_ARGS__)
+#define AGC_FAST_DIRECT(LAUNCHER, ...) AGC_FAST_ALL(LAUNCHER, __VA_ARGS__) AGC_FAST_LAUNCH(LAUNCHER, FM_MINMAX, __VA_ARGS__)
 
   // a CTA may take at most FAST_MAX_PER_CTA elements per launch (fixed-point / u32-count headroom): chunk N
   auto chunked = [&](int ctas, size_t smem, bool cache) {
@@ -250,7 +255,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
       p.labels = (const char*)r->index.labels + off * (i64 ? 8 : 4);
       p.a = need_a ? (const float*)r->a + off : nullptr;
       if (cache) { AGC_FAST_ALL(launch_cache, p, ctas, smem, st, sms) }
-      else { AGC_FAST_ALL(launch_fast, p, ctas, smem, st, sms) }
+      else { AGC_FAST_DIRECT(launch_fast, p, ctas, smem, st, sms) }
     }
     p.n = r->n; p.labels = r->index.labels; p.a = (const float*)r->a;
   };
@@ -441,6 +446,7 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
     }
     p.choose2 = nullptr; p.side = 0;
   }
+#undef AGC_FAST_DIRECT
 #undef AGC_FAST_ALL
 #undef AGC_FAST_LAUNCH
   return rc < 0 ? rc : 1;

@@ -23,7 +23,9 @@
 
 namespace agc {
 
-enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4, FM_SUM1 = 5, FM_SUMCNT1 = 6 };
+enum { FM_SUM = 0, FM_SUMCNT = 1, FM_MAX = 2, FM_MIN = 3, FM_LEN = 4, FM_SUM1 = 5, FM_SUMCNT1 = 6, FM_MINMAX = 7 };
+// FM_MINMAX: both extremes from one read of (labels, a) -- the fused multi-statistic pass (AGC_OP_MINMAX): max key in word 0,
+// min key in word 1, two native ATOMS per element; merged into T0 (max keys) and T2 (min keys, as int64)
 // FM_SUMCNT1: FM_SUM1's one-word sum + a u32 count (8 B per group instead of FM_SUMCNT's 12): mean / var on tables of 16.6 K - 24.9 K groups
 // FM_SUM1: ONE 32-bit word per group (k_fast only).  The word starts at 2^31 and takes q = x * 2^(FX1_F - E) with a
 // native ATOMS.ADD that returns the old value; a carry / borrow out of the word (the add crossed 0 or 2^32) is
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   __shared__ unsigned s_maxbits;
   constexpr bool ONEWORD = MODE == FM_SUM1 || MODE == FM_SUMCNT1;
   constexpr bool HAS_CNT = MODE == FM_SUMCNT || MODE == FM_SUMCNT1;
-  constexpr int WORDS = (MODE == FM_SUM || MODE == FM_SUMCNT1) ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
+  constexpr int WORDS = (MODE == FM_SUM || MODE == FM_SUMCNT1 || MODE == FM_MINMAX) ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
   constexpr bool IS_SUM = MODE == FM_SUM || MODE == FM_SUMCNT || ONEWORD;
   constexpr int FXF = ONEWORD ? FX1_F : FX_F, FXW = ONEWORD ? FX1_WINDOW : FX_WINDOW;
   const int rs = p.rshift;
@@ -116,8 +118,8 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
   unsigned* w1 = sw + G;        // sum.hi | count (FM_SUMCNT1)
   unsigned* w2 = sw + 2 * G;    // count (FM_SUMCNT)
   unsigned* wc = MODE == FM_SUMCNT1 ? w1 : w2;
-  const unsigned init0 = (MODE == FM_MAX || ONEWORD) ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
-  for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : 0u;   // G counts replicas
+  const unsigned init0 = (MODE == FM_MAX || MODE == FM_MINMAX || ONEWORD) ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
+  for (int i = threadIdx.x; i < WORDS * G; i += blockDim.x) sw[i] = (i < G) ? init0 : (MODE == FM_MINMAX ? 0x7fffffffu : 0u);   // G counts replicas
   // second pass of var / std with the means in shared memory: each mean as a (hi, lo) pair of floats (exact to 2^-48), so
   // that the deviation is two f32 subtractions instead of f64 arithmetic (relative error ~1e-7 per term, unbiased)
   // values outside the exact fixed-point window (huge / tiny / inf / NaN): on a small table their f64 REDs would queue
@@ -198,7 +200,10 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     const bool nan = x != x;
     if (LOAD_A && nan && nanskip) return;
     if (MODE == FM_LEN) { if (PARTIAL) red_add_u64_hint((unsigned long long*)(p.t.t1 + g), 1ull, pol); else atomicAdd((unsigned long long*)(p.t.t1 + g), 1ull); }
-    else if (MODE == FM_MAX || MODE == FM_MIN) {
+    else if (MODE == FM_MINMAX) {
+      const long long kmax = nan ? AGC_EMPTY_MIN : key_of((double)x), kmin = nan ? AGC_EMPTY_MAX : key_of((double)x);
+      atomicMax(p.t.t0i + g, kmax); atomicMin((long long*)p.t.t2 + g, kmin);
+    } else if (MODE == FM_MAX || MODE == FM_MIN) {
       const long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
       if (PARTIAL) { if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol); }
       else { if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64); }
@@ -222,6 +227,11 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     if (MODE == FM_LEN) {
       if (LOAD_A && nanskip && x != x) return;
       atomicAdd(w0 + gi, 1u);
+    } else if (MODE == FM_MINMAX) {
+      int kx, kn;
+      if (x != x) { if (nanskip) return; kx = 0x7fffffff; kn = (int)0x80000000; }           // NaN wins both
+      else kx = kn = key32_of(x);
+      atomicMax((int*)w0 + gi, kx); atomicMin((int*)w1 + gi, kn);
     } else if (MODE == FM_MAX || MODE == FM_MIN) {
       int k;
       if (x != x) { if (nanskip) return; k = MODE == FM_MAX ? 0x7fffffff : (int)0x80000000; }   // NaN wins
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
     update(LabelVec<LT>::one(p.labels, i), LOAD_A ? p.a[i] : 0.f);
   }
   if (bad) p.status[AGC_ST_BADLABEL] = 1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = MODE == FM_SUMCNT1 ? 19 : 10 + MODE;
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.status[AGC_ST_REGIME] = MODE == FM_SUMCNT1 ? 19 : (MODE == FM_MINMAX ? 30 : 10 + MODE);
   __syncthreads();
 
   // ---- merge the CTA's table into the global accumulator tables -----------------------------------
@@ -291,6 +301,11 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       unsigned long long c = 0;
       for (int r = 0; r < R; ++r) c += w0[e0 + r];
       if (c) atomicAdd((unsigned long long*)(p.t.t1 + gi), c);
+    } else if (MODE == FM_MINMAX) {
+      int kx = (int)0x80000000, kn = 0x7fffffff;
+      for (int r = 0; r < R; ++r) { kx = max(kx, (int)w0[e0 + r]); kn = min(kn, (int)w1[e0 + r]); }
+      if (kx != (int)0x80000000) atomicMax(p.t.t0i + gi, kx == 0x7fffffff ? AGC_EMPTY_MIN : key_of((double)unkey_f32(kx)));
+      if (kn != 0x7fffffff) atomicMin((long long*)p.t.t2 + gi, kn == (int)0x80000000 ? AGC_EMPTY_MAX : key_of((double)unkey_f32(kn)));
     } else if (MODE == FM_MAX || MODE == FM_MIN) {
       int k = (int)init0;
       for (int r = 0; r < R; ++r) { int kr = (int)w0[e0 + r]; k = MODE == FM_MAX ? max(k, kr) : min(k, kr); }

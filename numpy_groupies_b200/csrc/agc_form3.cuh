@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
     const int nr = p.rows - row0 < RB ? (int)(p.rows - row0) : RB;
 
     // reference exponent of this item from its first tile (see agc_fast.cuh)
-    unsigned lo_bits = 0, span_bits = 0; double scale = 1.0, inv_scale = 1.0;
+    unsigned lo_bits = 0, span_bits = 0; float scale_f = 1.f; double inv_scale = 1.0;
     if (IS_SUM) {
       unsigned m = 0;
       const long long v = v0 + threadIdx.x;
@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
       int lo_e = eb - FXW3; if (lo_e < 1) lo_e = 1;
       lo_bits = (unsigned)lo_e << 23;
       span_bits = (unsigned)(eb - lo_e) << 23;
-      scale = __longlong_as_double((long long)(1023 + FXF3 - (eb - 127)) << 52);
-      inv_scale = __longlong_as_double((long long)(1023 - FXF3 + (eb - 127)) << 52);
+      const int se = FXF3 - (eb - 127);                        // q = x * 2^se: an exact FMUL + F2I for in-window values (no f64 in the loop)
+      if (se < -126 || se > 127) span_bits = 0;                // scale not a normal float: everything takes the f64 RED
+      else scale_f = __int_as_float((se + 127) << 23);
+      inv_scale = __longlong_as_double((long long)(1023 - se) << 52);
     }
 
     auto update = [&](int gi, long long gflat, float x) {
@@ -100,8 +102,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
         if (nanskip && x != x) return;
         if (p.square) x = x * x;
         unsigned ab = __float_as_uint(x) & 0x7fffffffu;
-        if (ab - lo_bits < span_bits) fx_add(w0 + gi, w1 + gi, __double2ll_rn((double)x * scale));
-        else if (ab != 0u) atomicAdd(p.t.t0f + gflat, (double)x);      // out of window: exact f64 RED
+        if (ab - lo_bits < span_bits) {
+          const int q = __float2int_rn(x * scale_f);                    // |q| < 2^31, exact
+          const unsigned old = atomicAdd(w0 + gi, (unsigned)q);
+          const int net = (q >> 31) + (int)(old + (unsigned)q < old);   // carry (+1) / borrow (-1) into the high word
+          if (net) atomicAdd(w1 + gi, (unsigned)net);
+        } else if (ab != 0u) atomicAdd(p.t.t0f + gflat, (double)x);      // out of window: exact f64 RED
         if (MODE == FM_SUMCNT) atomicAdd(w2 + gi, 1u);
       }
     };

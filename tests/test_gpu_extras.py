@@ -289,3 +289,27 @@ def test_second_device_in_the_same_process():
                     np.testing.assert_array_equal(got.cpu().numpy(), r)
                 else:
                     np.testing.assert_allclose(got.cpu().numpy(), r, rtol=1e-5)
+
+
+@pytest.mark.parametrize("groups", [100, 4000, 24000, 60000])
+def test_fused_min_max_shared_memory_kernel(groups):
+    """AGC_OP_MINMAX on the shared-memory kernel (two key words per group, regime 30) up to 24.9 K groups, on the general
+    kernel beyond: min and max of aggregate_multi are bit-identical to the single calls, NaN / +-inf / empty groups included."""
+    import torch
+    rng = np.random.default_rng(groups)
+    n = (1 << 21) + 5
+    g = rng.integers(0, groups, n)
+    g[g == 11] = 12                                            # an empty group
+    a = rng.standard_normal(n).astype(np.float32)
+    a[rng.random(n) < 0.01] = np.nan
+    a[3], a[4] = np.inf, -np.inf
+    tg, ta = torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda()
+    for pre in ("", "nan"):
+        res = ac.aggregate_multi(tg, ta, [pre + "min", pre + "max"], size=groups, fill_value=-7)
+        if groups <= 24000:
+            assert ac.last_regime() in (30, 0), ac.last_regime()
+        for f in (pre + "min", pre + "max"):
+            one = aggregate(tg, ta, f, size=groups, fill_value=-7)
+            assert torch.equal(res[f].view(torch.int32), one.view(torch.int32)), f
+            with np.errstate(all="ignore"):
+                np.testing.assert_array_equal(res[f].cpu().numpy(), oracle.aggregate(g, a, func=f, size=groups, fill_value=-7))
