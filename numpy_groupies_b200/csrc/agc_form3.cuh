@@ -7,6 +7,12 @@
 // labels of a column vector ONCE and streams the RB rows under them, so label traffic is 8/RB bytes per element
 // and comes from L2.  Items are handed out through a device counter; each item ends with one RED per touched
 // (row, group) into the global tables of agc_generic.cuh, which keeps Forms 3/4 on the same finalise path.
+//
+// Bound (round 2): sums run at ~575 Gelem/s = 2 elements / clk / SM whatever the fixed-point layout -- a 31-bit grid whose
+// high word only moves on a carry (1.25 ATOMS per element, FMUL + F2I instead of f64 conversions) measured the SAME 1.87-1.95
+// ms for 4096 x 2^18 as the two-ATOMS 40-bit grid kept here: what counts is the ONE shared-memory atomic per element that
+// must RETURN the old word for the carry, and those retire at ~2 lanes / clk / SM (max / min, whose atomics return
+// nothing, run at 3.8).  The same rate is what Form 1 sums hide behind their 12 B / element of HBM traffic.
 #pragma once
 #include "agc_fast.cuh"
 
@@ -30,12 +36,6 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
   __shared__ int s_item;
   constexpr int WORDS = MODE == FM_SUM ? 2 : (MODE == FM_SUMCNT ? 3 : 1);
   constexpr bool IS_SUM = MODE == FM_SUM || MODE == FM_SUMCNT;
-  // Fixed-point grid of THIS kernel: 31 fraction bits, so |q| < 2^31 and the high word only moves on a carry out of the low
-  // one (~1.25 ATOMS per element instead of 2: the kernel is bound by the shared-memory atomic rate).  The price is an
-  // 7-binade exact window; what falls below it (0.8 % of rand() values) takes the f64 RED -- harmless HERE because the
-  // global table has rows x G entries (the same trick lost on Form 1 with 100 groups, where those REDs pile on 100
-  // addresses: agc_fast.cuh keeps 40 bits there).
-  constexpr int FXF3 = 31, FXW3 = FXF3 - 24;
   const int G = (int)p.G, T = RB * G;
   unsigned* w0 = sw; unsigned* w1 = sw + T; unsigned* w2 = sw + 2 * T;
   const unsigned init0 = MODE == FM_MAX ? 0x80000000u : (MODE == FM_MIN ? 0x7fffffffu : 0u);
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
     const int nr = p.rows - row0 < RB ? (int)(p.rows - row0) : RB;
 
     // reference exponent of this item from its first tile (see agc_fast.cuh)
-    unsigned lo_bits = 0, span_bits = 0; float scale_f = 1.f; double inv_scale = 1.0;
+    unsigned lo_bits = 0, span_bits = 0; double scale = 1.0, inv_scale = 1.0;
     if (IS_SUM) {
       unsigned m = 0;
       const long long v = v0 + threadIdx.x;
@@ -80,13 +80,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
       int eb = (int)(s_maxbits >> 23);
       if (eb == 0) eb = 127;
       eb += 1;
-      int lo_e = eb - FXW3; if (lo_e < 1) lo_e = 1;
+      int lo_e = eb - FX_WINDOW; if (lo_e < 1) lo_e = 1;
       lo_bits = (unsigned)lo_e << 23;
       span_bits = (unsigned)(eb - lo_e) << 23;
-      const int se = FXF3 - (eb - 127);                        // q = x * 2^se: an exact FMUL + F2I for in-window values (no f64 in the loop)
-      if (se < -126 || se > 127) span_bits = 0;                // scale not a normal float: everything takes the f64 RED
-      else scale_f = __int_as_float((se + 127) << 23);
-      inv_scale = __longlong_as_double((long long)(1023 - se) << 52);
+      scale = __longlong_as_double((long long)(1023 + FX_F - (eb - 127)) << 52);
+      inv_scale = __longlong_as_double((long long)(1023 - FX_F + (eb - 127)) << 52);
     }
 
     auto update = [&](int gi, long long gflat, float x) {
@@ -102,12 +100,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_form3(const Form3Params p) 
         if (nanskip && x != x) return;
         if (p.square) x = x * x;
         unsigned ab = __float_as_uint(x) & 0x7fffffffu;
-        if (ab - lo_bits < span_bits) {
-          const int q = __float2int_rn(x * scale_f);                    // |q| < 2^31, exact
-          const unsigned old = atomicAdd(w0 + gi, (unsigned)q);
-          const int net = (q >> 31) + (int)(old + (unsigned)q < old);   // carry (+1) / borrow (-1) into the high word
-          if (net) atomicAdd(w1 + gi, (unsigned)net);
-        } else if (ab != 0u) atomicAdd(p.t.t0f + gflat, (double)x);      // out of window: exact f64 RED
+        if (ab - lo_bits < span_bits) fx_add(w0 + gi, w1 + gi, __double2ll_rn((double)x * scale));
+        else if (ab != 0u) atomicAdd(p.t.t0f + gflat, (double)x);      // out of window: exact f64 RED
         if (MODE == FM_SUMCNT) atomicAdd(w2 + gi, 1u);
       }
     };
