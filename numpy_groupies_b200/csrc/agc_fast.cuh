@@ -205,12 +205,10 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       atomicMax(p.t.t0i + g, kmax); atomicMin((long long*)p.t.t2 + g, kmin);
     } else if (MODE == FM_MAX || MODE == FM_MIN) {
       const long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
-      if (PARTIAL) {
-        // monotone update: a plain (possibly stale) read decides whether the RED is needed at all.  A group of m elements sees
-        // ~ln(m) record highs, so at 10^7 groups (107 elements each) 95 % of the uncovered elements become an L2 read
-        // instead of a RED
-        const long long seen = __ldcg(p.t.t0i + g);
-        if (MODE == FM_MAX ? k64 > seen : k64 < seen) { if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol); }
+      // (test-then-update -- an L2 read of the current extreme before the RED -- was measured HERE and lost: max at 10^7 groups
+      //  6.8 -> 20.7 ms.  The read must return before the thread knows whether to send the RED, eight dependent round trips
+      //  per thread iteration; a RED is fire-and-forget.  The general kernel keeps it: there one element per thread is in flight.)
+      if (PARTIAL) { if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol); }
       } else { if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64); }
     } else {
       if (p.square) x = x * x;
@@ -625,8 +623,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 2) k_cache(const FastParams p) {
         if (MODE == FM_MAX) atomicMax((int*)w0 + s, k); else atomicMin((int*)w0 + s, k);
       } else {
         long long k64 = nan ? (MODE == FM_MAX ? AGC_EMPTY_MIN : AGC_EMPTY_MAX) : key_of((double)x);
-        const long long seen = __ldcg(p.t.t0i + g);            // test-then-update: most misses cannot improve the extreme
-        if (MODE == FM_MAX ? k64 > seen : k64 < seen) { if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol); }
+        if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol);
       }
     } else {
       const unsigned ab = __float_as_uint(x) & 0x7fffffffu;

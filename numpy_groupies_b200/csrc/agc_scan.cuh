@@ -761,95 +761,81 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_seg_scan_chain8: the chained scan as a PERSISTENT kernel with the next tile's loads in flight (int64 labels,
-// 8-byte values, full tiles).  The one-tile-per-CTA version above loads, scans, waits for its look-back and stores in
-// sequence: global loads are in flight during a quarter of a tile's life only, ~33 KB per SM on average, and the kernel
-// streams at the 2.9 TB/s that buys (ncu: 38 % of the stall samples at the barrier behind the look-back warp).  Here a CTA
-// walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and issues the 8 x 128-bit loads of its NEXT tile right after the
-// block scan of the current one -- they fly while warp 0 looks back and while the results are stored.  Two CTAs of 256
-// threads per SM (the raw loads stay in registers) keep 64 KB per SM in flight all the time.  Tiles past the last full
-// one (and every other dtype combination) go to k_seg_scan_direct<.., 2> with tile0 set; the descriptors are shared.
+// k_seg_scan_lean: the chained scan for the all-64-bit case (int64 labels, int64 / uint64 / float64 values, result of
+// the accumulator's own width, full tiles) with everything the general kernel decides at run time -- value dtype,
+// nan-skip, output conversion, ragged edges -- fixed at compile time.  The general PHASE-2 kernel executes 142 thread
+// instructions per element (ncu, r02e: ISETP / MOV / SEL / BRA for dtype switches and bounds it re-derives per element)
+// at 46 % issue utilisation: its 2.2 ms are as much instruction count as look-back latency.  VK: 0 int64, 1 uint64,
+// 2 float64 values.  Tiles past the last full one go to k_seg_scan_direct<.., 2> with tile0 set; the descriptors are shared.
+// (A persistent variant of this kernel with the next tile's loads in flight -- 128 registers, 2 CTAs per SM -- measured
+// 3.08 ms against 2.24: with two resident CTAs nothing runs while one waits for its look-back.)
 // ---------------------------------------------------------------------------------------------
-template <class A, int OP>
-__global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_chain8(const ScanParams p, unsigned long long* desc, int nfull) {
+template <class A, int OP, int VK, bool NANSKIP>
+__global__ void __launch_bounds__(SG_THREADS) k_seg_scan_lean(const ScanParams p, unsigned long long* desc) {
   __shared__ int4 s_stage[SG_THREADS / 32][128];
   __shared__ unsigned long long s_carry;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int tile = blockIdx.x;
+  if (__syncthreads_or(*(volatile const int*)p.unsorted)) {     // somebody found an inversion: the sort-based path redoes everything
+    if (threadIdx.x == 0) desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, 0ull);
+    return;
+  }
+  const long long base = (long long)tile * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
+  const long long wbase = (long long)tile * SG_TILE + (long long)wrp * (32 * SG_ITEMS);
   int4 raw_lab[4], raw_val[4];
-  int tile = blockIdx.x;
-  if (tile < nfull) {
-    const long long wb = (long long)tile * SG_TILE + (long long)wrp * (32 * SG_ITEMS);
-    warp_fetch8((const long long*)p.labels + wb, lane, raw_lab);
-    warp_fetch8((const unsigned long long*)p.a + wb, lane, raw_val);
-  }
-  const bool mm64 = (OP == SC_MAX || OP == SC_MIN) && !p.a_float && (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64);
-  const bool vst = !((uintptr_t)p.out & 15) &&
-                   (mm64 || ((OP == SC_SUM || OP == SC_PROD) &&
-                             (std::is_same<A, double>::value ? p.out_dtype == AGC_DT_F64 : (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64))));
-  const unsigned long long keyflip = (mm64 && p.a_u64) ? 0x8000000000000000ull : 0ull;
-  for (; tile < nfull; tile += gridDim.x) {
-    // labels not sorted (somebody found an inversion): the sort-based path redoes everything; publish what the others wait for
-    if (__syncthreads_or(*(volatile const int*)p.unsorted)) {
-      if (threadIdx.x == 0) for (int t = tile; t < nfull; t += gridDim.x) desc_store(desc + 2 * (long long)t, 2ull | 0x100ull, 0ull);
-      return;
-    }
-    const long long base = (long long)tile * SG_TILE + (long long)threadIdx.x * SG_ITEMS;
-    const long long wbase = (long long)tile * SG_TILE + (long long)wrp * (32 * SG_ITEMS);
-    unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
-    warp_transpose8(raw_lab, s_stage[wrp], lane, gl);
-    warp_transpose8(raw_val, s_stage[wrp], lane, raw);
-    long long prev = 0;
-    const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
-    if (lane > 0) prev = left;
-    else if (base > 0) prev = ((const long long*)p.labels)[base - 1];
-    A x[SG_ITEMS]; bool h[SG_ITEMS];
-    bool tf = false; A tx = A(0); bool uns = false, bad = false;
+  warp_fetch8((const long long*)p.labels + wbase, lane, raw_lab);
+  warp_fetch8((const unsigned long long*)p.a + wbase, lane, raw_val);
+  unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
+  warp_transpose8(raw_lab, s_stage[wrp], lane, gl);
+  warp_transpose8(raw_val, s_stage[wrp], lane, raw);
+  long long prev = 0;
+  const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
+  if (lane > 0) prev = left;
+  else if (base > 0) prev = ((const long long*)p.labels)[base - 1];
+  A x[SG_ITEMS]; unsigned hmask = 0;                           // bit k: element k opens a segment
+  A tx = A(0); bool uns = false, bad = false;
+  const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
 #pragma unroll
-    for (int k = 0; k < SG_ITEMS; ++k) {
-      const long long g = (long long)gl[k];
-      h[k] = (base + k == 0) || g != prev;
-      uns |= base + k > 0 && g < prev; bad |= g < 0 || g >= p.size;
-      prev = g;
-      x[k] = scan_from_raw<A, OP>(p, raw[k], h[k]);
-      if (k == 0) { tf = h[k]; tx = x[k]; }
-      else { if (h[k]) tx = x[k]; else tx = ScanOp<A, OP>::apply(tx, x[k]); tf = tf | h[k]; }
-      x[k] = tx;                                 // thread-local inclusive scan
-    }
-    if (uns) *p.unsorted_w = 1;
-    if (bad) p.status[AGC_ST_BADLABEL] = 1;
-    bool pf, have_p, agg_f; A px, agg_x;
-    block_seg_scan<A, OP>(tf, tx, pf, px, have_p, agg_f, agg_x);
-    // the next tile's loads: in flight during the look-back and the stores below
-    if (tile + (int)gridDim.x < nfull) {
-      const long long wb = (long long)(tile + gridDim.x) * SG_TILE + (long long)wrp * (32 * SG_ITEMS);
-      warp_fetch8((const long long*)p.labels + wb, lane, raw_lab);
-      warp_fetch8((const unsigned long long*)p.a + wb, lane, raw_val);
-    }
-    if (threadIdx.x < 32) {
-      if (lane == 0) desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
-      A c = A(0);
-      if (tile > 0) {
-        c = chain_lookback<A, OP>(desc, tile, lane, (unsigned)p.lb_sleep);
-        if (lane == 0) desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
-      }
-      if (lane == 0) s_carry = scan_bits<A>(c);
-    }
-    __syncthreads();
-    const bool have_c = tile > 0; const A cx = scan_unbits<A>(s_carry);
-    bool have = false; A pre = A(0);
-    if (have_p) { pre = px; have = true; if (have_c && !pf) pre = ScanOp<A, OP>::apply(cx, px); }
-    else if (have_c) { pre = cx; have = true; }
-    bool open = have;
-    unsigned long long ob[SG_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SG_ITEMS; ++k) {
-      if (h[k]) open = false;
-      const A r = open ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
-      if (!vst) scan_store<A, OP>(p, base + k, r);
-      ob[k] = std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : ((unsigned long long)(long long)r ^ keyflip);
-    }
-    if (vst) warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    const long long g = (long long)gl[k];
+    const bool head = (k == 0 && base == 0) || g != prev;
+    uns |= g < prev && !(k == 0 && base == 0);
+    bad |= (unsigned long long)g >= (unsigned long long)p.size;
+    prev = g;
+    A v;
+    if (VK == 2) { double d = __longlong_as_double((long long)raw[k]); if (NANSKIP && d != d) d = OP == SC_SUM ? 0.0 : 1.0; v = (A)d; }
+    else v = (A)(long long)(raw[k] ^ keyflip);                 // int64 as is; uint64 max / min: order-preserving key
+    tx = (k == 0 || head) ? v : ScanOp<A, OP>::apply(tx, v);
+    hmask |= head ? (1u << k) : 0u;
+    x[k] = tx;                                                 // thread-local inclusive scan
   }
+  if (uns) *p.unsorted_w = 1;
+  if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  bool pf, have_p, agg_f; A px, agg_x;
+  block_seg_scan<A, OP>(hmask != 0u, tx, pf, px, have_p, agg_f, agg_x);
+  if (threadIdx.x < 32) {
+    if (lane == 0) desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+    A c = A(0);
+    if (tile > 0) {
+      c = chain_lookback<A, OP>(desc, tile, lane, (unsigned)p.lb_sleep);
+      if (lane == 0) desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
+    }
+    if (lane == 0) s_carry = scan_bits<A>(c);
+  }
+  __syncthreads();
+  const bool have_c = tile > 0; const A cx = scan_unbits<A>(s_carry);
+  bool have = false; A pre = A(0);
+  if (have_p) { pre = px; have = true; if (have_c && !pf) pre = ScanOp<A, OP>::apply(cx, px); }
+  else if (have_c) { pre = cx; have = true; }
+  // the prefix applies to the elements before this thread's first segment head
+  const int nopen = !have ? 0 : (hmask ? __ffs((int)hmask) - 1 : SG_ITEMS);
+  unsigned long long ob[SG_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    const A r = k < nopen ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
+    ob[k] = (std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : (unsigned long long)(long long)r) ^ keyflip;
+  }
+  warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
 }
 
 // single block: segmented scan over the tile aggregates -> carry for tile t = aggregate of tiles [0, t).
@@ -1051,16 +1037,22 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
   if (scan_chain_enabled() && !(p.flags & AGC_F_DETERMINISTIC)) {          // one pass, 24 B/element: tile descriptors + warp-parallel look-back
     cudaMemsetAsync(ws + L.desc, 0, (size_t)ntiles * 16, st);
     int nfull = 0;
-    // (the persistent variant with the next tile's loads in flight measured SLOWER -- 3.08 against 2.24 ms for cumsum at
-    //  N = 2^28, profiles/r02f_scan_*.jsonl: two CTAs of 128 registers per SM leave nothing to run while a CTA waits for its
-    //  look-back -- and stays behind AGC_SCAN_PERSIST=1 as a record of the experiment)
-    static const bool persist = getenv("AGC_SCAN_PERSIST") && atoi(getenv("AGC_SCAN_PERSIST")) == 1;
-    if (persist && sizeof(LT) == 8 && dtype_bytes(p.a_dtype) == 8 && !((uintptr_t)p.a & 15)) {
-      // full tiles of the all-64-bit case: persistent kernel, next tile's loads in flight (2 CTAs per SM)
-      nfull = (int)(p.n / SG_TILE);
-      if (nfull > 0) {
-        const int grid = nfull < 2 * device_sms() ? nfull : 2 * device_sms();
-        AGC_COUNT_LAUNCH(1), k_seg_scan_chain8<A, OP><<<grid, SG_THREADS, 0, st>>>(p, (unsigned long long*)(ws + L.desc), nfull);
+    // full tiles of the all-64-bit case (the C4 configuration): the lean kernel, everything decided at compile time
+    {
+      const bool i64v = p.a_dtype == AGC_DT_I64, u64v = p.a_dtype == AGC_DT_U64, f64v = p.a_dtype == AGC_DT_F64;
+      const bool ints = std::is_same<A, long long>::value && (i64v || u64v) && (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64);
+      const bool flts = std::is_same<A, double>::value && f64v && p.out_dtype == AGC_DT_F64 && (OP == SC_SUM || OP == SC_PROD);
+      static const bool lean_on = !(getenv("AGC_SCAN_LEAN") && atoi(getenv("AGC_SCAN_LEAN")) == 0);
+      if (lean_on && sizeof(LT) == 8 && (ints || flts) && !((uintptr_t)p.a & 15) && !((uintptr_t)p.out & 15)) {
+        nfull = (int)(p.n / SG_TILE);
+        if (nfull > 0) {
+          unsigned long long* d = (unsigned long long*)(ws + L.desc);
+          const bool ns = (p.flags & AGC_F_NANSKIP) != 0;
+          AGC_COUNT_LAUNCH(1);
+          if (flts) { if (ns) k_seg_scan_lean<A, OP, 2, true><<<nfull, SG_THREADS, 0, st>>>(p, d); else k_seg_scan_lean<A, OP, 2, false><<<nfull, SG_THREADS, 0, st>>>(p, d); }
+          else if (u64v) k_seg_scan_lean<A, OP, 1, false><<<nfull, SG_THREADS, 0, st>>>(p, d);
+          else k_seg_scan_lean<A, OP, 0, false><<<nfull, SG_THREADS, 0, st>>>(p, d);
+        }
       }
     }
     if (nfull < ntiles) {
