@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(FAST_THREADS, U == 1 ? 2 : 1) k_fast(const Fas
       //  6.8 -> 20.7 ms.  The read must return before the thread knows whether to send the RED, eight dependent round trips
       //  per thread iteration; a RED is fire-and-forget.  The general kernel keeps it: there one element per thread is in flight.)
       if (PARTIAL) { if (MODE == FM_MAX) red_max_s64_hint(p.t.t0i + g, k64, pol); else red_min_s64_hint(p.t.t0i + g, k64, pol); }
-      } else { if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64); }
+      else { if (MODE == FM_MAX) atomicMax(p.t.t0i + g, k64); else atomicMin(p.t.t0i + g, k64); }
     } else {
       if (p.square) x = x * x;
       if ((__float_as_uint(x) & 0x7fffffffu) != 0u) { if (PARTIAL) red_add_f64_hint(p.t.t0f + g, (double)x, pol); else atomicAdd(p.t.t0f + g, (double)x); }

@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
 // 3.08 ms against 2.24: with two resident CTAs nothing runs while one waits for its look-back.)
 // ---------------------------------------------------------------------------------------------
 template <class A, int OP, int VK, bool NANSKIP>
-__global__ void __launch_bounds__(SG_THREADS) k_seg_scan_lean(const ScanParams p, unsigned long long* desc) {
+__global__ void __launch_bounds__(SG_THREADS, 6) k_seg_scan_lean(const ScanParams p, unsigned long long* desc) {
   __shared__ int4 s_stage[SG_THREADS / 32][128];
   __shared__ unsigned long long s_carry;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
