@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
 // (A persistent variant of this kernel with the next tile's loads in flight -- 128 registers, 2 CTAs per SM -- measured
 // 3.08 ms against 2.24: with two resident CTAs nothing runs while one waits for its look-back.)
 // ---------------------------------------------------------------------------------------------
-template <class A, int OP, int VK, bool NANSKIP>
-__global__ void __launch_bounds__(SG_THREADS, 6) k_seg_scan_lean(const ScanParams p, unsigned long long* desc) {
+template <class A, int OP, int VK, bool NANSKIP, int OCC>
+__global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_lean(const ScanParams p, unsigned long long* desc) {
   __shared__ int4 s_stage[SG_THREADS / 32][128];
   __shared__ unsigned long long s_carry;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -1049,9 +1049,18 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
           unsigned long long* d = (unsigned long long*)(ws + L.desc);
           const bool ns = (p.flags & AGC_F_NANSKIP) != 0;
           AGC_COUNT_LAUNCH(1);
-          if (flts) { if (ns) k_seg_scan_lean<A, OP, 2, true><<<nfull, SG_THREADS, 0, st>>>(p, d); else k_seg_scan_lean<A, OP, 2, false><<<nfull, SG_THREADS, 0, st>>>(p, d); }
-          else if (u64v) k_seg_scan_lean<A, OP, 1, false><<<nfull, SG_THREADS, 0, st>>>(p, d);
-          else k_seg_scan_lean<A, OP, 0, false><<<nfull, SG_THREADS, 0, st>>>(p, d);
+          // resident CTAs per SM (register budget 65536 / (256 * OCC)): the kernel is bound by loads in flight, more CTAs win
+          // until the spills bite (measured at N = 2^28, cumsum: 5 CTAs / 48 registers 1.66 ms, 6 / 40 1.55 ms)
+          static const int occ = getenv("AGC_SCAN_OCC") ? atoi(getenv("AGC_SCAN_OCC")) : 6;
+#define AGC_LEAN(VK_, NS_)                                                                                              \
+          { if (occ >= 8) k_seg_scan_lean<A, OP, VK_, NS_, 8><<<nfull, SG_THREADS, 0, st>>>(p, d);                          \
+            else if (occ == 7) k_seg_scan_lean<A, OP, VK_, NS_, 7><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
+            else if (occ == 5) k_seg_scan_lean<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
+            else k_seg_scan_lean<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d); }
+          if (flts) { if (ns) AGC_LEAN(2, true) else AGC_LEAN(2, false) }
+          else if (u64v) AGC_LEAN(1, false)
+          else AGC_LEAN(0, false)
+#undef AGC_LEAN
         }
       }
     }

@@ -1,0 +1,145 @@
+// red_probe.cu -- round-2 micro-probe: what does ONE scattered global RED cost the SM when only part of a warp
+// issues it (the partial-table kernels: 42-50 % of the lanes), and does staging the uncovered elements in a
+// per-warp shared-memory queue so that every RED instruction leaves with 32 active lanes make it cheaper?
+// Not part of the product path.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o red_probe red_probe.cu && ./red_probe [log2N=28]
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+__global__ void gen_uniform(long long* idx, float* a, long long n, long long G, uint64_t seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint64_t h = mix64(i ^ seed);
+    idx[i] = (long long)(h % (uint64_t)G);
+    a[i] = (float)((mix64(h) >> 40) * (1.0 / 16777216.0));
+  }
+}
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+  int4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+    : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r;
+}
+__device__ __forceinline__ void red_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+
+// MODE 0: no shared table; elements with g >= cov send a RED from wherever they sit (partial warps), others are dropped
+// MODE 1: same, but staged through a per-warp queue: every RED instruction has 32 active lanes
+// MODE 2: covered elements do a native ATOMS.ADD on the shared table, uncovered RED in place
+// MODE 3: covered ATOMS, uncovered staged
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k_probe(const long long* __restrict__ idx, const float* __restrict__ a,
+                                                   long long n, double* tab, int cov, int qoff_words) {
+  extern __shared__ unsigned su[];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  if (MODE >= 2) { for (int i = threadIdx.x; i < cov; i += blockDim.x) su[i] = 0u; }
+  // per-warp queue: 64 records of (group, value bits)
+  uint2* q = reinterpret_cast<uint2*>(su + qoff_words) + wrp * 64;
+  int fill = 0;
+  __syncthreads();
+  const long long nvec = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec + stride; v += stride) {
+    const bool live = v < nvec;   // keep whole warps in the loop so that the ballots stay convergent
+    int4 l0 = make_int4(0, 0, 0, 0), l1 = l0, av = l0;
+    if (live) {
+      l0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v);
+      l1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v + 1);
+      av = ldg_stream(reinterpret_cast<const int4*>(a) + v);
+    }
+    const int g4[4] = {l0.x, l0.z, l1.x, l1.z};
+    const int x4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = g4[j];
+      const bool unc = live && g >= cov;
+      if (MODE >= 2) { if (live && g < cov) atomicAdd(&su[g], (unsigned)x4[j] >> 20); }
+      if (MODE == 0 || MODE == 2) {
+        if (unc) red_f64(tab + g, (double)__int_as_float(x4[j]));
+      } else {
+        const unsigned m = __ballot_sync(0xffffffffu, unc);
+        if (unc) q[fill + __popc(m & ((1u << lane) - 1u))] = make_uint2((unsigned)g, (unsigned)x4[j]);
+        fill += __popc(m);
+        if (fill >= 32) {
+          __syncwarp();
+          fill -= 32;
+          const uint2 r = q[fill + lane];
+          red_f64(tab + r.x, (double)__uint_as_float(r.y));
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (MODE == 1 || MODE == 3) {
+    __syncwarp();
+    if (lane < fill) { const uint2 r = q[lane]; red_f64(tab + r.x, (double)__uint_as_float(r.y)); }
+  }
+  if (MODE >= 2) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < cov; i += blockDim.x) if (su[i]) red_f64(tab + i, (double)su[i]);
+  }
+}
+
+template <class L> static double time_ms(L launch, int warm = 2, int reps = 5) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int i = 0; i < warm; ++i) launch();
+  CK(cudaDeviceSynchronize());
+  double best = 1e30;
+  for (int i = 0; i < reps; ++i) {
+    cudaEventRecord(a); launch(); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  return best;
+}
+
+int main(int argc, char** argv) {
+  int lg = argc > 1 ? atoi(argv[1]) : 28;
+  long long N = 1ll << lg;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  int sms = prop.multiProcessorCount;
+  long long* idx; float* a; double* tab;
+  CK(cudaMalloc(&idx, N * 8)); CK(cudaMalloc(&a, N * 4));
+  const long long G = 100000;
+  CK(cudaMalloc(&tab, G * 8)); CK(cudaMemset(tab, 0, G * 8));
+  gen_uniform<<<sms * 8, 256>>>(idx, a, N, G, 100);
+  CK(cudaDeviceSynchronize());
+  const int SMEM_MAX = 227 * 1024;
+  CK(cudaFuncSetAttribute((const void*)k_probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+  CK(cudaFuncSetAttribute((const void*)k_probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+  CK(cudaFuncSetAttribute((const void*)k_probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+  CK(cudaFuncSetAttribute((const void*)k_probe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+  const int QB = 32 * 64 * 8;   // queue bytes per CTA
+  // (smem bytes in total, covered groups): under the 196 KB carve-out cliff and above it
+  struct Cfg { int smem; int cov; } cfgs[] = {
+    {199552, (199552 - QB) / 4}, {199552, 199552 / 4}, {231424, (231424 - QB) / 4}, {231424, 231424 / 4},
+    {199552, 0}, {199552, 25000}, {199552, 75000}};
+  for (const Cfg& c : cfgs) {
+    for (int mode = 0; mode < 4; ++mode) {
+      const bool staged = mode == 1 || mode == 3;
+      int cov = c.cov;
+      if (cov * 4 + (staged ? QB : 0) > c.smem) continue;
+      const int qoff = (c.smem - QB) / 4;
+      double ms = time_ms([&] {
+        if (mode == 0) k_probe<0><<<sms, 1024, c.smem>>>(idx, a, N, tab, cov, qoff);
+        if (mode == 1) k_probe<1><<<sms, 1024, c.smem>>>(idx, a, N, tab, cov, qoff);
+        if (mode == 2) k_probe<2><<<sms, 1024, c.smem>>>(idx, a, N, tab, cov, qoff);
+        if (mode == 3) k_probe<3><<<sms, 1024, c.smem>>>(idx, a, N, tab, cov, qoff);
+      });
+      const double unc = 1.0 - (double)cov / G;
+      printf("{\"smem\": %d, \"cov\": %d, \"uncovered\": %.3f, \"mode\": \"%s\", \"ms\": %.3f, \"gelem_s\": %.1f, \"g_red_s\": %.1f}\n",
+             c.smem, cov, unc,
+             mode == 0 ? "drop+red" : mode == 1 ? "drop+staged red" : mode == 2 ? "atoms+red" : "atoms+staged red",
+             ms, N / ms * 1e-6, unc * N / ms * 1e-6);
+      fflush(stdout);
+    }
+  }
+  return 0;
+}
