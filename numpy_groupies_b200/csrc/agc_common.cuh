@@ -1,6 +1,7 @@
 // agc_common.cuh -- shared device helpers for libaggcuda (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <stdint.h>
 #include <atomic>
 #include "../../include/aggcuda.h"

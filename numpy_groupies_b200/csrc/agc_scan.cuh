@@ -838,6 +838,342 @@ __global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_lean(const ScanPar
   warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_seg_scan_warp: the chained scan with the WARP as the chained unit.  ncu on k_seg_scan_lean (r2j): half of all warp
+// time is spent at the CTA barriers -- seven warps wait for the slowest warp's loads, then all eight wait for warp 0's
+// look-back -- and a tile lives 8 us of which its loads are in flight for 2.5.  Here every warp owns a 256-element tile
+// with its own descriptor: it loads, scans with shuffles, publishes, looks back over the 32 warp tiles before it and
+// stores, without ever meeting another warp at a barrier.  Warp tiles are numbered blockIdx * 8 + warp, CTAs start in
+// blockIdx order and all warps of a CTA are resident together, so every descriptor a warp waits for belongs to a warp
+// that is running or done.  The last warp of a CTA also publishes the CTA-level descriptor the tail kernel
+// (k_seg_scan_direct<.., 2>, the ragged last tile) looks back at.
+// ---------------------------------------------------------------------------------------------
+template <class A, int OP>
+__device__ __forceinline__ A chain_lookback_near(const unsigned long long* desc, int t, int lane, unsigned sleep_ns) {
+  A acc = A(0); bool have = false;
+  int look = t - 1 - lane;
+  for (;;) {
+    unsigned long long m = 2ull, xb = 0ull;                    // tiles before tile 0 never matter
+    if (look >= 0) desc_load(desc + 2 * (long long)look, m, xb);
+    int first;
+    for (;;) {                                                 // wait only for the descriptors up to the nearest terminator seen so far
+      const bool pub = (m & 3ull) != 0ull;
+      const bool term = pub && ((m & 3ull) == 2ull || (m & 0x100ull) != 0ull);
+      const unsigned pb = __ballot_sync(0xffffffffu, pub), tb = __ballot_sync(0xffffffffu, term);
+      first = tb ? __ffs((int)tb) - 1 : 32;
+      const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+      if ((pb & need) == need) break;
+      if (!pub && lane <= first) {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        desc_load(desc + 2 * (long long)look, m, xb);
+      }
+    }
+    A x = scan_unbits<A>(xb);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                         // lane i ends with the fold of lanes [i, first], farthest first
+      const A y = __shfl_down_sync(0xffffffffu, x, o);
+      if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+    }
+    const A win = __shfl_sync(0xffffffffu, x, 0);
+    acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
+    if (first < 32) break;
+    look -= 32;
+  }
+  return acc;
+}
+
+template <class A, int OP, int VK, bool NANSKIP, int OCC>
+__global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_warp(const ScanParams p, unsigned long long* desc_cta, unsigned long long* desc) {
+  __shared__ int4 s_stage[SG_THREADS / 32][128];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int wt = (int)blockIdx.x * (SG_THREADS / 32) + wrp;      // this warp's tile
+  if (*(volatile const int*)p.unsorted) {                        // somebody found an inversion: the sort-based path redoes everything
+    if (lane == 0) {
+      desc_store(desc + 2 * (long long)wt, 2ull | 0x100ull, 0ull);
+      if (wrp == SG_THREADS / 32 - 1) desc_store(desc_cta + 2 * (long long)blockIdx.x, 2ull | 0x100ull, 0ull);
+    }
+    return;
+  }
+  const long long wbase = (long long)wt * (32 * SG_ITEMS);
+  const long long base = wbase + (long long)lane * SG_ITEMS;
+  int4 raw_lab[4], raw_val[4];
+  warp_fetch8((const long long*)p.labels + wbase, lane, raw_lab);
+  warp_fetch8((const unsigned long long*)p.a + wbase, lane, raw_val);
+  long long prev0 = 0;
+  if (lane == 0 && wbase > 0) prev0 = ((const long long*)p.labels)[wbase - 1];
+  unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
+  warp_transpose8(raw_lab, s_stage[wrp], lane, gl);
+  warp_transpose8(raw_val, s_stage[wrp], lane, raw);
+  const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
+  long long prev = lane > 0 ? left : prev0;
+  A x[SG_ITEMS]; unsigned hmask = 0;                           // bit k: element k opens a segment
+  A tx = A(0); bool uns = false, bad = false;
+  const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    const long long g = (long long)gl[k];
+    const bool head = (k == 0 && base == 0) || g != prev;
+    uns |= g < prev && !(k == 0 && base == 0);
+    bad |= (unsigned long long)g >= (unsigned long long)p.size;
+    prev = g;
+    A v;
+    if (VK == 2) { double d = __longlong_as_double((long long)raw[k]); if (NANSKIP && d != d) d = OP == SC_SUM ? 0.0 : 1.0; v = (A)d; }
+    else v = (A)(long long)(raw[k] ^ keyflip);                 // int64 as is; uint64 max / min: order-preserving key
+    tx = (k == 0 || head) ? v : ScanOp<A, OP>::apply(tx, v);
+    hmask |= head ? (1u << k) : 0u;
+    x[k] = tx;                                                 // thread-local inclusive scan
+  }
+  if (uns) *p.unsorted_w = 1;
+  if (bad) p.status[AGC_ST_BADLABEL] = 1;
+  // inclusive segmented scan of the 32 thread aggregates
+  bool fi = hmask != 0u; A xi = tx;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const bool ft = __shfl_up_sync(0xffffffffu, (int)fi, o);
+    const A xt = __shfl_up_sync(0xffffffffu, xi, o);
+    if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
+  }
+  const bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); const A xe = __shfl_up_sync(0xffffffffu, xi, 1);
+  const bool agg_f = __shfl_sync(0xffffffffu, (int)fi, 31); const A agg_x = __shfl_sync(0xffffffffu, xi, 31);
+  if (lane == 0) desc_store(desc + 2 * (long long)wt, (wt == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+  A c = A(0);
+  if (wt > 0) c = chain_lookback_near<A, OP>(desc, wt, lane, (unsigned)p.lb_sleep);
+  if (lane == 0) {
+    const unsigned long long incl = scan_bits<A>((agg_f || wt == 0) ? agg_x : ScanOp<A, OP>::apply(c, agg_x));
+    if (wt > 0) desc_store(desc + 2 * (long long)wt, 2ull | 0x100ull, incl);
+    if (wrp == SG_THREADS / 32 - 1) desc_store(desc_cta + 2 * (long long)blockIdx.x, 2ull | 0x100ull, incl);
+  }
+  const bool have_c = wt > 0;
+  bool have = false; A pre = A(0);
+  if (lane > 0) { pre = xe; have = true; if (have_c && !fe) pre = ScanOp<A, OP>::apply(c, xe); }
+  else if (have_c) { pre = c; have = true; }
+  // the prefix applies to the elements before this thread's first segment head
+  const int nopen = !have ? 0 : (hmask ? __ffs((int)hmask) - 1 : SG_ITEMS);
+  unsigned long long ob[SG_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SG_ITEMS; ++k) {
+    const A r = k < nopen ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
+    ob[k] = (std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : (unsigned long long)(long long)r) ^ keyflip;
+  }
+  warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_seg_scan_pipe: the chained scan as a PERSISTENT kernel fed by the TMA.  What the one-tile-per-CTA kernels above cannot
+// fix is their duty cycle: a tile has its loads in flight for ~2.5 us of an 8 us life, and even the plain two-pass kernels
+// (no chain at all) stream at 4.5-5.3 TB/s.  Here a CTA of 256 threads walks the tiles round robin with the rest of the grid
+// (all CTAs are resident, so every tile a look-back waits for is being worked on), and its thread 0 keeps
+// the loads of the next SP_STAGES - 1 tiles in flight with cp.async.bulk into a ring in shared memory (complete_tx on one
+// mbarrier per stage: 16 KB of labels, 16 KB of values, and the 16 bytes before the tile for the label left of it) -- the
+// bytes in flight no longer depend on what the threads are doing.  The threads read their 8 consecutive elements from the
+// linear buffers in a rotated order (unit (k + t/2) % 4 at step k: conflict-free 128-bit accesses) and rotate the
+// registers back.  The look-back is software-pipelined: a tile publishes its aggregate as soon as its block scan is done,
+// but its own look-back runs one iteration later -- the descriptor loads are issued before the next tile's data is touched
+// and by then every predecessor has published -- so no thread ever waits for the chain.  Results leave through a 16 KB
+// buffer with one bulk store per tile.  3 stages * 32 KB + 16 KB = 112 KB per CTA, two CTAs per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int SP_STAGES = 3;
+constexpr int SP_IN_BYTES = SG_TILE * 8;                         // one array of one tile
+// 7 tile buffers (3 stages of labels + values, one for the results) at a 512-byte aligned address, then the mbarriers and
+// the "label left of the tile" slots
+constexpr int SP_SMEM = (2 * SP_STAGES + 1) * SP_IN_BYTES + 512 + SP_STAGES * 16 + 64;
+__device__ __forceinline__ unsigned sp_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void sp_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void sp_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_store(void* dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sp_store_read_done() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void sp_store_done() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sp_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sp_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void sp_tensor_load(unsigned dst, const void* tmap, int row, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(dst), "l"(tmap), "r"(0), "r"(row), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sp_tensor_store(const void* tmap, int row, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" :: "l"(tmap), "r"(0), "r"(row), "r"(src) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// The tile buffers are filled by the TMA as boxes of 256 rows x 64 bytes with the 64-byte swizzle: the 16-byte unit k of
+// row r lives at unit k ^ ((r >> 1) & 3) of the row (address bits 4-5 ^= bits 7-8; the buffers are 512-byte aligned).
+// Row t is exactly thread t's 8 consecutive elements, and the XOR makes the quarter-warps' 128-bit accesses conflict
+// free -- the registers come out in element order with no shuffling at all.  (A linear buffer read in a rotated order and
+// rotated back in registers cost 200 of the kernel's 674 instructions per warp and tile.)
+__device__ __forceinline__ void sp_read8(const int4* buf, int t, unsigned long long (&out)[SG_ITEMS]) {
+  const int r = (t >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int4 u = buf[4 * t + (j ^ r)];
+    out[2 * j] = ((unsigned long long)(unsigned)u.x) | ((unsigned long long)(unsigned)u.y << 32);
+    out[2 * j + 1] = ((unsigned long long)(unsigned)u.z) | ((unsigned long long)(unsigned)u.w << 32);
+  }
+}
+__device__ __forceinline__ void sp_write8(int4* buf, int t, const unsigned long long (&in)[SG_ITEMS]) {
+  const int r = (t >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    buf[4 * t + (j ^ r)] = make_int4((int)(unsigned)in[2 * j], (int)(in[2 * j] >> 32), (int)(unsigned)in[2 * j + 1], (int)(in[2 * j + 1] >> 32));
+}
+// look-back with the first window's descriptors already requested (m, xb)
+template <class A, int OP>
+__device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, int t, int lane, unsigned long long m, unsigned long long xb) {
+  A acc = A(0); bool have = false;
+  int look = t - 1 - lane;
+  for (;;) {
+    int first;
+    for (;;) {                                                 // wait only for the descriptors up to the nearest terminator seen so far
+      const bool pub = (m & 3ull) != 0ull;
+      const bool term = pub && ((m & 3ull) == 2ull || (m & 0x100ull) != 0ull);
+      const unsigned pb = __ballot_sync(0xffffffffu, pub), tb = __ballot_sync(0xffffffffu, term);
+      first = tb ? __ffs((int)tb) - 1 : 32;
+      const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+      if ((pb & need) == need) break;
+      if (!pub && lane <= first) desc_load(desc + 2 * (long long)look, m, xb);
+    }
+    A x = scan_unbits<A>(xb);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {                         // lane i ends with the fold of lanes [i, first], farthest first
+      const A y = __shfl_down_sync(0xffffffffu, x, o);
+      if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+    }
+    const A win = __shfl_sync(0xffffffffu, x, 0);
+    acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
+    if (first < 32) break;
+    look -= 32;
+    m = 2ull; xb = 0ull;                                       // tiles before tile 0 never matter
+    if (look >= 0) desc_load(desc + 2 * (long long)look, m, xb);
+  }
+  return acc;
+}
+
+template <class A, int OP, int VK, bool NANSKIP>
+__global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_pipe(const ScanParams p, unsigned long long* desc, int nfull,
+                                                                 const __grid_constant__ CUtensorMap tm_lab, const __grid_constant__ CUtensorMap tm_val,
+                                                                 const __grid_constant__ CUtensorMap tm_out) {
+  extern __shared__ __align__(128) unsigned char sp_dyn[];
+  unsigned char* sp_raw = sp_dyn + ((512u - (sp_saddr(sp_dyn) & 511u)) & 511u);      // the swizzle pattern is a function of the address
+  int4* s_in = (int4*)sp_raw;                                            // [stage][labels | values][1024 units]
+  int4* s_out = (int4*)(sp_raw + SP_STAGES * 2 * SP_IN_BYTES);
+  int4* s_left = (int4*)(sp_raw + SP_STAGES * 2 * SP_IN_BYTES + SP_IN_BYTES);   // [stage]: the 16 bytes before the tile's labels
+  unsigned long long* s_bar = (unsigned long long*)(s_left + SP_STAGES);
+  __shared__ unsigned long long s_carry;
+  const int t = threadIdx.x, lane = t & 31;
+  const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
+  // tiles go round robin: iteration `it` of CTA b owns tile it * gridDim + b, so that neighbouring tiles are worked on at
+  // the same time by neighbouring CTAs (with tickets taken at prefetch time CTA 0 held tiles 0, 1, 2 and CTA 1 waited two
+  // iterations for tile 2 before it could finish tile 3, and so on down the grid: a start-up ramp of half the run time).
+  // All CTAs of the grid (two per SM) are resident together, so every tile a look-back waits for is being worked on.
+  const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+  auto issue = [&](int s, int tile) {                                    // thread 0: the loads of one tile into stage s
+    const unsigned bar = sp_saddr(s_bar + s);
+    sp_expect_tx(bar, 2 * SP_IN_BYTES + (tile > 0 ? 16 : 0));
+    sp_tensor_load(sp_saddr(s_in + (2 * s) * (SG_TILE / 2)), &tm_lab, tile * SG_THREADS, bar);
+    sp_tensor_load(sp_saddr(s_in + (2 * s + 1) * (SG_TILE / 2)), &tm_val, tile * SG_THREADS, bar);
+    if (tile > 0) sp_bulk_load(sp_saddr(s_left + s), (const long long*)p.labels + (long long)tile * SG_TILE - 2, 16, bar);
+  };
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < SP_STAGES; ++s) sp_mbar_init(sp_saddr(s_bar + s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sp_fence_async();
+#pragma unroll
+    for (int s = 0; s < SP_STAGES; ++s) { const int tile = s * grid + cta; if (tile < nfull) issue(s, tile); }
+  }
+  __syncthreads();
+  // the tile whose results are still owed (its look-back runs one iteration late)
+  bool owe = false; int tp = 0;
+  A xp[SG_ITEMS]; unsigned hmask_p = 0; bool pf_p = false, have_p_p = false, aggf_p = false; A px_p = A(0), aggx_p = A(0);
+  auto settle = [&](unsigned long long m, unsigned long long xb) {       // finish tile tp: look-back, prefix, results, bulk store
+    if (t < 32) {
+      A c = A(0);
+      if (tp > 0) {
+        c = chain_lookback_pre<A, OP>(desc, tp, lane, m, xb);
+        if (lane == 0) desc_store(desc + 2 * (long long)tp, 2ull | 0x100ull, scan_bits<A>(aggf_p ? aggx_p : ScanOp<A, OP>::apply(c, aggx_p)));
+      }
+      if (lane == 0) { s_carry = scan_bits<A>(c); sp_store_read_done(); }    // the previous bulk store has read s_out
+    }
+    __syncthreads();
+    const bool have_c = tp > 0; const A cx = scan_unbits<A>(s_carry);
+    bool have = false; A pre = A(0);
+    if (have_p_p) { pre = px_p; have = true; if (have_c && !pf_p) pre = ScanOp<A, OP>::apply(cx, px_p); }
+    else if (have_c) { pre = cx; have = true; }
+    const int nopen = !have ? 0 : (hmask_p ? __ffs((int)hmask_p) - 1 : SG_ITEMS);
+    unsigned long long ob[SG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) {
+      const A r = k < nopen ? ScanOp<A, OP>::apply(pre, xp[k]) : xp[k];
+      ob[k] = (std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : (unsigned long long)(long long)r) ^ keyflip;
+    }
+    sp_write8(s_out, t, ob);
+    sp_fence_async();
+    __syncthreads();
+    if (t == 0) sp_tensor_store(&tm_out, tp * SG_THREADS, sp_saddr(s_out));
+  };
+  for (int it = 0;; ++it) {
+    const int s = it % SP_STAGES;
+    const unsigned parity = (unsigned)(it / SP_STAGES) & 1u;
+    const int tile = it * grid + cta;
+    if (tile >= nfull) break;
+    unsigned long long lm = 2ull, lxb = 0ull;                            // look-back of the owed tile: request its window now
+    if (owe && t < 32 && tp - 1 - lane >= 0) desc_load(desc + 2 * (long long)(tp - 1 - lane), lm, lxb);
+    sp_mbar_wait(sp_saddr(s_bar + s), parity);
+    unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
+    sp_read8(s_in + (2 * s) * (SG_TILE / 2), t, gl);
+    sp_read8(s_in + (2 * s + 1) * (SG_TILE / 2), t, raw);
+    const long long base = (long long)tile * SG_TILE + (long long)t * SG_ITEMS;
+    long long prev = 0;
+    const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
+    if (lane > 0) prev = left;
+    else if (t > 0) { const int4 q = (s_in + (2 * s) * (SG_TILE / 2))[4 * (t - 1) + (3 ^ (((t - 1) >> 1) & 3))]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
+    else if (tile > 0) { const int4 q = s_left[s]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
+    A x[SG_ITEMS]; unsigned hmask = 0;
+    A tx = A(0); bool uns = false, bad = false;
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) {
+      const long long g = (long long)gl[k];
+      const bool head = (k == 0 && base == 0) || g != prev;
+      uns |= g < prev && !(k == 0 && base == 0);
+      bad |= (unsigned long long)g >= (unsigned long long)p.size;
+      prev = g;
+      A v;
+      if (VK == 2) { double d = __longlong_as_double((long long)raw[k]); if (NANSKIP && d != d) d = OP == SC_SUM ? 0.0 : 1.0; v = (A)d; }
+      else v = (A)(long long)(raw[k] ^ keyflip);
+      tx = (k == 0 || head) ? v : ScanOp<A, OP>::apply(tx, v);
+      hmask |= head ? (1u << k) : 0u;
+      x[k] = tx;
+    }
+    if (uns) *p.unsorted_w = 1;                                          // (the kernel finishes its pass anyway: every tile publishes)
+    if (bad) p.status[AGC_ST_BADLABEL] = 1;
+    bool pf, have_p, agg_f; A px, agg_x;
+    block_seg_scan<A, OP>(hmask != 0u, tx, pf, px, have_p, agg_f, agg_x);   // every thread is past its reads of stage s after this
+    if (t == 0) {
+      desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+      const int next = (it + SP_STAGES) * grid + cta;
+      if (next < nfull) issue(s, next);
+    }
+    if (owe) settle(lm, lxb);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) xp[k] = x[k];
+    hmask_p = hmask; pf_p = pf; have_p_p = have_p; px_p = px; aggf_p = agg_f; aggx_p = agg_x; tp = tile; owe = true;
+  }
+  if (owe) {
+    unsigned long long lm = 2ull, lxb = 0ull;
+    if (t < 32 && tp - 1 - lane >= 0) desc_load(desc + 2 * (long long)(tp - 1 - lane), lm, lxb);
+    settle(lm, lxb);
+  }
+  if (t == 0) sp_store_done();
+}
+
 // single block: segmented scan over the tile aggregates -> carry for tile t = aggregate of tiles [0, t).
 // (f, x) (+) (g, y) = (f | g, g ? y : op(x, y)).  Tile 0 always starts with a head flag, so every exclusive prefix
 // with t > 0 is well defined.  The tiles are walked in coalesced chunks of 1024 with a running carry; the next
@@ -977,7 +1313,7 @@ inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   w.hist = take(256ll * nb * 4); w.tsum = take((xs_tiles(256ll * nb) + 1) * 4);
   const long long ntiles = (n + SG_TILE - 1) / SG_TILE + 1;
   w.tile_f = take(ntiles); w.tile_x = take(ntiles * 8); w.carry_f = take(ntiles); w.carry_x = take(ntiles * 8);
-  w.desc = take(ntiles * 16);
+  w.desc = take(ntiles * 16 * (1 + SG_THREADS / 32));     // CTA-level descriptors, then one per warp tile (k_seg_scan_warp)
   w.flag = take(256);
   w.total = o;
   return w;
@@ -1026,6 +1362,26 @@ inline bool scan_chain_enabled() {
   if (g_scan_chain < 0) { const char* e = getenv("AGC_SCAN_CHAIN"); g_scan_chain = (e && atoi(e) == 0) ? 0 : 1; }
   return g_scan_chain != 0;
 }
+// tensor map of an array of 8-byte elements seen as rows of 8 (64 bytes); one box = one tile = 256 rows
+typedef CUresult (*sp_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline sp_encode_fn sp_encoder() {
+  static sp_encode_fn fn = [] {
+    void* f = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (sp_encode_fn)f;
+  }();
+  return fn;
+}
+inline bool sp_tile_map(CUtensorMap* tm, const void* base, int nfull) {
+  sp_encode_fn enc = sp_encoder();
+  if (!enc || nfull <= 0) return false;
+  const cuuint64_t dims[2] = {8, (cuuint64_t)nfull * SG_THREADS};
+  const cuuint64_t strides[1] = {64};
+  const cuuint32_t box[2] = {8, SG_THREADS}, estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 template <class A, int OP, class LT>
 inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st) {
   if (p.n == 0) return;
@@ -1050,17 +1406,31 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
           const bool ns = (p.flags & AGC_F_NANSKIP) != 0;
           AGC_COUNT_LAUNCH(1);
           // resident CTAs per SM (register budget 65536 / (256 * OCC)): the kernel is bound by loads in flight, more CTAs win
-          // until the spills bite (measured at N = 2^28, cumsum: 5 CTAs / 48 registers 1.66 ms, 6 / 40 1.55 ms)
+          // until the spills bite (k_seg_scan_lean at N = 2^28, cumsum: 5 CTAs / 48 registers 1.66 ms, 6 / 40 1.55 ms)
           static const int occ = getenv("AGC_SCAN_OCC") ? atoi(getenv("AGC_SCAN_OCC")) : 6;
+          static const bool warp_on = getenv("AGC_SCAN_WARP") && atoi(getenv("AGC_SCAN_WARP")) != 0;   // measured: 1.68 ms against 1.55 for the CTA-tile kernel
+          unsigned long long* dw = d + 2 * (long long)ntiles;    // warp-tile descriptors
+          static const bool pipe_env = !(getenv("AGC_SCAN_PIPE") && atoi(getenv("AGC_SCAN_PIPE")) == 0);
+          CUtensorMap tml, tmv, tmo;                             // 256 rows x 64 bytes per tile, 64-byte swizzle
+          const bool pipe_on = pipe_env && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo, p.out, nfull);
+          if (warp_on && !pipe_on) cudaMemsetAsync(dw, 0, (size_t)nfull * (SG_THREADS / 32) * 16, st);
+          const int pgrid = nfull < 2 * device_sms() ? nfull : 2 * device_sms();
+#define AGC_PIPE(VK_, NS_)                                                                                              \
+          { static std::atomic<unsigned long long> attr_done{0};                                                           \
+            ensure_dyn_smem(k_seg_scan_pipe<A, OP, VK_, NS_>, SP_SMEM, attr_done);                                         \
+            k_seg_scan_pipe<A, OP, VK_, NS_><<<pgrid, SG_THREADS, SP_SMEM, st>>>(p, d, nfull, tml, tmv, tmo); }
 #define AGC_LEAN(VK_, NS_)                                                                                              \
-          { if (occ >= 8) k_seg_scan_lean<A, OP, VK_, NS_, 8><<<nfull, SG_THREADS, 0, st>>>(p, d);                          \
-            else if (occ == 7) k_seg_scan_lean<A, OP, VK_, NS_, 7><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
+          { if (pipe_on) AGC_PIPE(VK_, NS_)                                                                                \
+            else if (warp_on) {                                                                                            \
+              if (occ == 5) k_seg_scan_warp<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d, dw);                    \
+              else k_seg_scan_warp<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d, dw); }                           \
             else if (occ == 5) k_seg_scan_lean<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
             else k_seg_scan_lean<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d); }
           if (flts) { if (ns) AGC_LEAN(2, true) else AGC_LEAN(2, false) }
           else if (u64v) AGC_LEAN(1, false)
           else AGC_LEAN(0, false)
 #undef AGC_LEAN
+#undef AGC_PIPE
         }
       }
     }

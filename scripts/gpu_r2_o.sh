@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out/r2p
+timeout 900 python -m pytest tests/test_gpu_large.py -m gpu -q -x -k "sorted_label_scans or n_to_n or unsorted" > gpurun_out/r2p/pytest_scan.log 2>&1
+tail -3 gpurun_out/r2p/pytest_scan.log | cut -c1-300
+timeout 200 python scripts/one_scan.py 28 > gpurun_out/r2p/plain_scan.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_seg_scan_pipe -s 2 -c 1 -o gpurun_out/r2p/prof_scan_pipe python scripts/one_scan.py 28 > gpurun_out/r2p/ncu_scan.log 2>&1
+tail -2 gpurun_out/r2p/ncu_scan.log

@@ -164,6 +164,40 @@ def test_int64_n_to_n_bit_exact(func, dist):
     np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("groups", [3, 700, 40000, 2000000])
+@pytest.mark.parametrize("n", [(1 << 22) + 777, 1 << 21, 2048 * 3 + 5])
+def test_sorted_label_scans_chained_kernel(n, groups):
+    """Sorted int64 labels go through the single-pass chained scan: one descriptor per 256-element warp tile, look-back over
+    32 tiles at a time.  3 groups = chains thousands of tiles long (every look-back walks several windows), 2 * 10^6 groups
+    = a head in almost every tile; ragged N exercises the tail kernel behind the full tiles.  Bit-exact for the integers."""
+    rng = np.random.default_rng(n % 1000 + groups)
+    gidx = np.sort(rng.integers(0, groups, n))
+    a = rng.integers(-2**40, 2**40, n)
+    for func in ("cumsum", "cummax", "cummin"):
+        np.testing.assert_array_equal(aggregate(gidx, a, func=func, size=groups), oracle.aggregate(gidx, a, func=func, size=groups))
+    small = rng.integers(-2, 3, n)
+    np.testing.assert_array_equal(aggregate(gidx, small, func="cumprod", size=groups), oracle.aggregate(gidx, small, func="cumprod", size=groups))
+    u = rng.integers(0, 2**63, n).astype(np.uint64) * np.uint64(2) + np.uint64(1)          # values above 2^63: the order-preserving key matters
+    for func in ("cummax", "cummin"):
+        got = aggregate(gidx, u, func=func, size=groups)
+        ref = oracle.aggregate(gidx, u, func=func, size=groups)
+        assert got.dtype == ref.dtype
+        np.testing.assert_array_equal(got, ref)
+    # f64 running sums: the reference takes ONE np.cumsum over the whole array and subtracts each group's offset
+    # (aggregate_numpy.py:258-265), so ITS rounding error follows the global running sum (~n / 2 here), not the group's;
+    # the scan adds per group in a tree, the reference sequentially over up to 1.4 * 10^6 terms.  Allowed: eps * (global sum)
+    # absolute plus rtol 1e-10 (sequential f64 summation of 10^6 terms of one sign is itself only good to ~1e-11).
+    atol = 4 * 2.2e-16 * n
+    f = rng.random(n)
+    np.testing.assert_allclose(aggregate(gidx, f, func="cumsum", size=groups), oracle.aggregate(gidx, f, func="cumsum", size=groups), rtol=1e-10, atol=atol)
+    f[rng.random(n) < 0.1] = np.nan
+    np.testing.assert_allclose(aggregate(gidx, f, func="nancumsum", size=groups), oracle.aggregate(gidx, f, func="nancumsum", size=groups), rtol=1e-10, atol=atol)
+    # one inversion in the middle of the array: the chained kernel must notice and the sort-based path must take over
+    g2 = gidx.copy()
+    g2[n // 2], g2[n // 2 + 1] = groups - 1, 0
+    np.testing.assert_array_equal(aggregate(g2, a, func="cumsum", size=groups), oracle.aggregate(g2, a, func="cumsum", size=groups))
+
+
 @pytest.mark.parametrize("func", ["first", "last", "argmax", "argmin", "nanargmax", "any", "all", "prod", "nanfirst"])
 def test_other_reductions_f64(func):
     rng = np.random.default_rng(31)
