@@ -199,6 +199,13 @@ int         agc_ordered_accumulate(const agc_request_t* req, const int64_t* orde
  * every rank the owner's bits); unpack stores them into out[g] for every non-empty group. */
 int         agc_owner_pack(const agc_request_t* req, int64_t* carrier, int32_t unpack, void* stream);
 
+/* Host side of the H2D path for numpy labels (the reference hands `group_idx` to its kernels as it is,
+ * aggregate_numpy.py:370-392; here the labels have to cross PCIe first, and for int64 labels that is 8 of the 12 bytes
+ * per element): narrows n 8-byte integer labels (AGC_DT_I64 / AGC_DT_U64) to int32 into dst -- typically a page-locked
+ * staging buffer -- mapping every label outside [0, 2^31) to -1, which the kernels report as a bad label exactly like
+ * the original value.  Pure host code, thread-safe, no CUDA call; callers run it on slices from several threads. */
+int         agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_t* dst);
+
 /* measurement hooks (bench.py): when enabled, agc_aggregate brackets its dominant accumulate kernel with
  * CUDA events on the caller's stream; agc_profile_last_ms() waits for that kernel and returns its duration.
  * agc_launch_count() = number of libaggcuda kernels launched by this process so far. */

@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -130,7 +131,9 @@ def _tensor_np_dtype(t):
 _STAGE = {"bufs": None, "pool": None, "events": None}
 _STAGE_CHUNK = 32 << 20          # bytes per pinned staging buffer
 _STAGE_BUFS = 3
-_STAGE_THREADS = 4
+# host threads that fill the staging buffers (memcpy / label narrowing release the GIL): half the cores, at most 8
+_STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(2, min(8, (os.cpu_count() or 4) // 2))
+_NARROW_LABELS = os.environ.get("AGC_NARROW_LABELS", "1") != "0"
 
 
 def _stage_setup():
@@ -143,30 +146,72 @@ def _stage_setup():
     return _STAGE
 
 
-def _upload_staged(src_u8, dst_u8):
-    """Pageable host bytes -> device at close to PCIe rate: a ring of pinned staging buffers, filled by a few host
-    threads (numpy's memcpy releases the GIL) while the previous chunk's asynchronous H2D copy is in flight.
-    (A plain copy from pageable memory runs at ~14 GB/s: the driver stages it through one small buffer, single-threaded.)"""
+def _stage_ring(n_items, item_bytes, fill, dst_u8):
+    """Host data -> device through the ring of pinned staging buffers: `fill(stage_u8, lo, hi)` writes items [lo, hi) of
+    the source into a staging buffer (called from the pool's threads on slices of a chunk) while the previous chunk's
+    asynchronous H2D copy is in flight."""
     torch = _t()
     st = _stage_setup()
     bufs, events, pool = st["bufs"], st["events"], st["pool"]
-    n = src_u8.shape[0]
+    per_chunk = _STAGE_CHUNK // item_bytes
     k = 0
-    for off in range(0, n, _STAGE_CHUNK):
-        m = min(_STAGE_CHUNK, n - off)
+    for off in range(0, n_items, per_chunk):
+        m = min(per_chunk, n_items - off)
         i = k % _STAGE_BUFS
         if events[i] is not None:
             events[i].synchronize()                        # the copy that last read this buffer is done
         stage = bufs[i].numpy()
         step = -(-m // _STAGE_THREADS)
-        futs = [pool.submit(np.copyto, stage[j:min(j + step, m)], src_u8[off + j:off + min(j + step, m)]) for j in range(0, m, step)]
+        step = -(-step // 64) * 64                         # slices start on cache-line multiples of the staging buffer
+        futs = [pool.submit(fill, stage[j * item_bytes:min(j + step, m) * item_bytes], off + j, off + min(j + step, m))
+                for j in range(0, m, step)]
         for f in futs:
             f.result()
-        dst_u8[off:off + m].copy_(bufs[i][:m], non_blocking=True)
+        dst_u8[off * item_bytes:(off + m) * item_bytes].copy_(bufs[i][:m * item_bytes], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         events[i] = ev
         k += 1
+
+
+def _upload_staged(src_u8, dst_u8):
+    """Pageable host bytes -> device at close to PCIe rate.  (A plain copy from pageable memory runs at ~14 GB/s: the
+    driver stages it through one small buffer, single-threaded.)"""
+    _stage_ring(src_u8.shape[0], 1, lambda stage, lo, hi: np.copyto(stage, src_u8[lo:hi]), dst_u8)
+
+
+def _is_pinned_np(arr):
+    """Does this numpy array live in page-locked memory (e.g. a view of a pinned torch tensor)?"""
+    import warnings
+    try:
+        view = arr.view(_SIGNED_VIEW[arr.dtype.name]) if arr.dtype.name in _SIGNED_VIEW else arr
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                 # (read-only memory: we never write through this tensor)
+            return bool(_t().from_numpy(view).is_pinned())
+    except Exception:                                       # noqa: BLE001
+        return False
+
+
+def _upload_labels_narrowed(arr, device):
+    """Flat int64 / uint64 labels with a known size < 2^31 cross PCIe as int32: 8 of the 12 bytes per element of a
+    Form 1 call are labels, and the link, not the kernel, bounds a host-array call.  The pool's threads narrow slices
+    into the pinned ring (agc_host_narrow_labels: labels outside [0, 2^31) become -1 and are reported as bad labels like
+    the originals) while the previous chunk is on the wire; the kernels take int32 labels as they are."""
+    torch = _t()
+    lib = _abi.load()
+    arr = np.ascontiguousarray(arr).reshape(-1)
+    n = arr.shape[0]
+    code = _abi.dtype_code(arr.dtype)
+    base = arr.ctypes.data
+
+    def fill(stage, lo, hi):
+        rc = lib.agc_host_narrow_labels(base + lo * 8, code, hi - lo, stage.ctypes.data)
+        if rc:
+            raise RuntimeError(_abi.last_error())
+    with torch.cuda.device(device):
+        out = torch.empty(n, dtype=torch.int32, device=device)
+        _stage_ring(n, 4, fill, out.view(torch.uint8))
+    return _Dev(out, np.int32)
 
 
 def _upload(arr, device):
@@ -429,7 +474,19 @@ def _stream_ptr(device):
 def _labels_on_device(c, device):
     if getattr(c, "_labels_dev", None) is None:
         g = c.group_idx
-        c._labels_dev = _from_tensor(g) if _is_tensor(g) else _upload(g, device)
+        if _is_tensor(g):
+            c._labels_dev = _from_tensor(g)
+        else:
+            plan = getattr(c, "plan", None)                 # (not there yet while size=None is being resolved)
+            g = np.asanyarray(g)
+            # pageable int64 labels of a Form 1 call with a known size are narrowed to int32 by the staging threads (they
+            # touch every byte anyway); page-locked arrays go as they are, one DMA (narrowing them measured slower: the
+            # host threads move 37 GB/s here, the link 54)
+            if (_NARROW_LABELS and plan is not None and plan.form == "flat" and not plan.needs_size and 0 < plan.flat_size < 2 ** 31
+                    and g.dtype.kind in "iu" and g.dtype.itemsize == 8 and g.nbytes >= (8 << 20) and not _is_pinned_np(g)):
+                c._labels_dev = _upload_labels_narrowed(g, device)
+            else:
+                c._labels_dev = _upload(g, device)
     return c._labels_dev
 
 
@@ -499,8 +556,8 @@ def _run_device(c):
     lib = _abi.load()
     device = _device_of(c)
     plan = c.plan
-    lab = _labels_on_device(c, device)
-    vals = _values_on_device(c, device)
+    vals = _values_on_device(c, device)                    # first: a page-locked `a` is one asynchronous DMA, already on the
+    lab = _labels_on_device(c, device)                      # wire while the host threads narrow / stage the labels
     base = c.base
     n_out = plan.n if base in _N_TO_N else plan.flat_size
     out_np_dtype = c.out_dtype

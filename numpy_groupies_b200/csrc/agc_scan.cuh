@@ -1041,10 +1041,12 @@ __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, 
       if (!pub && lane <= first) desc_load(desc + 2 * (long long)look, m, xb);
     }
     A x = scan_unbits<A>(xb);
+    if (first > 0) {                                           // (the tile right before is a terminator: its value is the carry)
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {                         // lane i ends with the fold of lanes [i, first], farthest first
-      const A y = __shfl_down_sync(0xffffffffu, x, o);
-      if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+      for (int o = 1; o < 32; o <<= 1) {                       // lane i ends with the fold of lanes [i, first], farthest first
+        const A y = __shfl_down_sync(0xffffffffu, x, o);
+        if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
+      }
     }
     const A win = __shfl_sync(0xffffffffu, x, 0);
     acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
@@ -1060,7 +1062,7 @@ template <class A, int OP, int VK, bool NANSKIP>
 __global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_pipe(const ScanParams p, unsigned long long* desc, int nfull,
                                                                  const __grid_constant__ CUtensorMap tm_lab, const __grid_constant__ CUtensorMap tm_val,
                                                                  const __grid_constant__ CUtensorMap tm_out) {
-  extern __shared__ __align__(128) unsigned char sp_dyn[];
+  extern __shared__ __align__(16) unsigned char sp_dyn[];          // (a larger alignment here would pad the static shared memory of EVERY kernel in this translation unit)
   unsigned char* sp_raw = sp_dyn + ((512u - (sp_saddr(sp_dyn) & 511u)) & 511u);      // the swizzle pattern is a function of the address
   int4* s_in = (int4*)sp_raw;                                            // [stage][labels | values][1024 units]
   int4* s_out = (int4*)(sp_raw + SP_STAGES * 2 * SP_IN_BYTES);

@@ -232,6 +232,15 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
 }
 
 int agc_profile_enable(int on) { g_profile = on != 0; for (auto& pe : g_prof) pe.valid = false; return 0; }
+int agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_t* dst) {
+  if (src_dtype != AGC_DT_I64 && src_dtype != AGC_DT_U64) return fail(-1, "agc_host_narrow_labels: 8-byte integer labels only");
+  const unsigned long long* s = (const unsigned long long*)src;
+  for (int64_t i = 0; i < n; ++i) {                       // branch-free: vectorises
+    const unsigned long long v = s[i];
+    dst[i] = (v >> 31) ? -1 : (int32_t)v;
+  }
+  return 0;
+}
 float agc_profile_last_ms(void) {
   ProfEvents& pe = g_prof[g_prof_last_dev];
   if (!pe.valid) return -1.f;

@@ -52,3 +52,22 @@ def test_no_cpu_fallback_without_cuda():
     from numpy_groupies_b200 import aggregate
     with pytest.raises(RuntimeError):
         aggregate(np.array([0, 1, 1]), np.array([1.0, 2.0, 3.0]))
+
+
+def test_host_label_narrowing_is_pure_host_code():
+    """agc_host_narrow_labels (the host half of the H2D path for numpy labels) needs no GPU: int64 / uint64 -> int32,
+    everything outside [0, 2^31) becomes -1 (which the kernels report as a bad label, like the original value)."""
+    import numpy as np
+    lib = abi.load()
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 2**31, 100_003)
+    src[[5, 77, 1000]] = [-1, 2**31, -2**63]
+    dst = np.empty(src.shape[0], dtype=np.int32)
+    assert lib.agc_host_narrow_labels(src.ctypes.data, abi.dtype_code(src.dtype), src.shape[0], dst.ctypes.data) == 0
+    ref = np.where((src < 0) | (src >= 2**31), -1, src).astype(np.int32)
+    np.testing.assert_array_equal(dst, ref)
+    u = src.astype(np.uint64)                                # negative values wrap to >= 2^63: still out of range
+    assert lib.agc_host_narrow_labels(u.ctypes.data, abi.dtype_code(u.dtype), u.shape[0], dst.ctypes.data) == 0
+    np.testing.assert_array_equal(dst, ref)
+    i32 = src.astype(np.int32)
+    assert lib.agc_host_narrow_labels(i32.ctypes.data, abi.dtype_code(i32.dtype), 4, dst.ctypes.data) != 0
