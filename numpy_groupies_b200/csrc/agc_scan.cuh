@@ -557,6 +557,13 @@ __device__ __forceinline__ void desc_store(unsigned long long* d, unsigned long 
 __device__ __forceinline__ void desc_load(const unsigned long long* d, unsigned long long& meta, unsigned long long& xbits) {
   asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(meta), "=l"(xbits) : "l"(d) : "memory");
 }
+// the same with GPU scope instead of the system scope `volatile` implies (experiment: AGC_DESC_GPU=1)
+__device__ __forceinline__ void desc_store_gpu(unsigned long long* d, unsigned long long meta, unsigned long long xbits) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(d), "l"(meta), "l"(xbits) : "memory");
+}
+__device__ __forceinline__ void desc_load_gpu(const unsigned long long* d, unsigned long long& meta, unsigned long long& xbits) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(meta), "=l"(xbits) : "l"(d) : "memory");
+}
 template <class A> __device__ __forceinline__ unsigned long long scan_bits(A x);
 template <> __device__ __forceinline__ unsigned long long scan_bits<long long>(long long x) { return (unsigned long long)x; }
 template <> __device__ __forceinline__ unsigned long long scan_bits<double>(double x) { return (unsigned long long)__double_as_longlong(x); }
@@ -711,7 +718,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan_direct(const ScanParams
       if (lane == 0) desc_store(desc + 2 * (long long)t, (t == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
       A c = A(0);
       if (t > 0) {
-        c = chain_lookback<A, OP>(desc, t, lane, (unsigned)p.lb_sleep);
+        c = chain_lookback<A, OP>(desc, t, lane, (unsigned)p.lb_sleep & 0xffffu);
         if (lane == 0) desc_store(desc + 2 * (long long)t, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
       }
       if (lane == 0) s_carry = scan_bits<A>(c);
@@ -817,7 +824,7 @@ __global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_lean(const ScanPar
     if (lane == 0) desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
     A c = A(0);
     if (tile > 0) {
-      c = chain_lookback<A, OP>(desc, tile, lane, (unsigned)p.lb_sleep);
+      c = chain_lookback<A, OP>(desc, tile, lane, (unsigned)p.lb_sleep & 0xffffu);
       if (lane == 0) desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x)));
     }
     if (lane == 0) s_carry = scan_bits<A>(c);
@@ -937,7 +944,7 @@ __global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_warp(const ScanPar
   const bool agg_f = __shfl_sync(0xffffffffu, (int)fi, 31); const A agg_x = __shfl_sync(0xffffffffu, xi, 31);
   if (lane == 0) desc_store(desc + 2 * (long long)wt, (wt == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
   A c = A(0);
-  if (wt > 0) c = chain_lookback_near<A, OP>(desc, wt, lane, (unsigned)p.lb_sleep);
+  if (wt > 0) c = chain_lookback_near<A, OP>(desc, wt, lane, (unsigned)p.lb_sleep & 0xffffu);
   if (lane == 0) {
     const unsigned long long incl = scan_bits<A>((agg_f || wt == 0) ? agg_x : ScanOp<A, OP>::apply(c, agg_x));
     if (wt > 0) desc_store(desc + 2 * (long long)wt, 2ull | 0x100ull, incl);
@@ -1026,7 +1033,8 @@ __device__ __forceinline__ void sp_write8(int4* buf, int t, const unsigned long 
 }
 // look-back with the first window's descriptors already requested (m, xb)
 template <class A, int OP>
-__device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, int t, int lane, unsigned long long m, unsigned long long xb) {
+__device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, int t, int lane, unsigned long long m, unsigned long long xb,
+                                                unsigned sleep_ns = 0, bool gpu_scope = false) {
   A acc = A(0); bool have = false;
   int look = t - 1 - lane;
   for (;;) {
@@ -1038,7 +1046,8 @@ __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, 
       first = tb ? __ffs((int)tb) - 1 : 32;
       const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
       if ((pb & need) == need) break;
-      if (!pub && lane <= first) desc_load(desc + 2 * (long long)look, m, xb);
+      if (sleep_ns) __nanosleep(sleep_ns);
+      if (!pub && lane <= first) { if (gpu_scope) desc_load_gpu(desc + 2 * (long long)look, m, xb); else desc_load(desc + 2 * (long long)look, m, xb); }
     }
     A x = scan_unbits<A>(xb);
     if (first > 0) {                                           // (the tile right before is a terminator: its value is the carry)
@@ -1053,7 +1062,7 @@ __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, 
     if (first < 32) break;
     look -= 32;
     m = 2ull; xb = 0ull;                                       // tiles before tile 0 never matter
-    if (look >= 0) desc_load(desc + 2 * (long long)look, m, xb);
+    if (look >= 0) { if (gpu_scope) desc_load_gpu(desc + 2 * (long long)look, m, xb); else desc_load(desc + 2 * (long long)look, m, xb); }
   }
   return acc;
 }
@@ -1174,6 +1183,193 @@ __global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_pipe(const ScanParam
     settle(lm, lxb);
   }
   if (t == 0) sp_store_done();
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_seg_scan_ws: k_seg_scan_pipe without a single CTA-wide barrier -- the same TMA ring, tiles and descriptors, but the
+// block-level part of the scan, the look-back and the loads belong to a NINTH warp.  ncu on k_seg_scan_pipe (r2q): the
+// memory pipeline never runs dry (its mbarrier wait succeeds at the first try, always); what bounds the kernel is the
+// serial path of a CTA through one tile -- four barriers, the warp-0 look-back with seven warps waiting (28 % of all
+// stall samples), the serial folds of the block scan -- 2.4 us per 2048 elements, two CTAs per SM.  Here
+//   * the 8 data warps read their 256 elements, scan them with shuffles, hand (flag, value) of the warp to the ninth
+//     warp through shared memory + an mbarrier arrive, and go straight on to the NEXT tile; one tile later they pick up
+//     their warp's exclusive prefix (carry included), finish the owed results and store their own 2 KB slice with a
+//     32-row tensor store -- warps drift freely, nothing waits for the slowest warp;
+//   * the ninth warp waits for the 8 arrivals, scans the 8 warp aggregates, refills the stage the tile occupied (its
+//     readers have all arrived), publishes the tile's descriptor, runs the look-back (requested before the wait), publishes
+//     the prefix and posts the 8 warp prefixes.
+// Slots are double-buffered by tile parity; a data warp is at most one tile ahead of the ninth warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_THREADS = SG_THREADS + 32;
+constexpr int WS_SMEM = 115712;                                   // two CTAs per SM: (228 KB - 2 * 1 KB reserved) / 2; 496 B of small state + alignment + 7 tile buffers
+__device__ __forceinline__ void sp_mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+
+template <class A, int OP, int VK, bool NANSKIP>
+__global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams p, unsigned long long* desc, int nfull,
+                                                               const __grid_constant__ CUtensorMap tm_lab, const __grid_constant__ CUtensorMap tm_val,
+                                                               const __grid_constant__ CUtensorMap tm_out32) {
+  extern __shared__ __align__(16) unsigned char sp_dyn[];
+  // small state first (496 bytes), then the tile buffers at the next 512-byte boundary (the swizzle is a function of the address)
+  int4* s_left = (int4*)sp_dyn;                                          // [stage]: the 16 bytes before the tile's labels
+  unsigned long long* s_bar = (unsigned long long*)(s_left + SP_STAGES); // full[3], agg_ready[2], prefix_ready[2]
+  unsigned long long* s_aggx = s_bar + 8;                                // [2][8]
+  unsigned long long* s_prex = s_aggx + 16;                              // [2][8]
+  unsigned* s_aggf = (unsigned*)(s_prex + 16);                           // [2][8]
+  unsigned* s_preh = s_aggf + 16;                                        // [2][8]: does warp w have a prefix at all
+  unsigned char* sp_raw = sp_dyn + ((sp_saddr(sp_dyn) + 496u + 511u) & ~511u) - sp_saddr(sp_dyn);
+  int4* s_in = (int4*)sp_raw;                                            // [stage][labels | values][1024 units]
+  int4* s_out = (int4*)(sp_raw + SP_STAGES * 2 * SP_IN_BYTES);           // [warp][128 units]
+  const int t = threadIdx.x, lane = t & 31, wrp = t >> 5;
+  const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+  const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
+  const unsigned bar_full = sp_saddr(s_bar), bar_agg = sp_saddr(s_bar + 3), bar_pre = sp_saddr(s_bar + 5);
+  const unsigned sleep_ns = (unsigned)p.lb_sleep & 0xffffu; const bool gpu_scope = (p.lb_sleep >> 30) & 1;
+  auto issue = [&](int s, int tile) {
+    const unsigned bar = bar_full + 8 * s;
+    sp_expect_tx(bar, 2 * SP_IN_BYTES + (tile > 0 ? 16 : 0));
+    sp_tensor_load(sp_saddr(s_in + (2 * s) * (SG_TILE / 2)), &tm_lab, tile * SG_THREADS, bar);
+    sp_tensor_load(sp_saddr(s_in + (2 * s + 1) * (SG_TILE / 2)), &tm_val, tile * SG_THREADS, bar);
+    if (tile > 0) sp_bulk_load(sp_saddr(s_left + s), (const long long*)p.labels + (long long)tile * SG_TILE - 2, 16, bar);
+  };
+  if (t == SG_THREADS) {                                                 // lane 0 of the ninth warp sets everything up
+#pragma unroll
+    for (int s = 0; s < SP_STAGES; ++s) sp_mbar_init(bar_full + 8 * s, 1);
+    sp_mbar_init(bar_agg, SG_THREADS / 32); sp_mbar_init(bar_agg + 8, SG_THREADS / 32);
+    sp_mbar_init(bar_pre, 1); sp_mbar_init(bar_pre + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sp_fence_async();
+#pragma unroll
+    for (int s = 0; s < SP_STAGES; ++s) { const int tile = s * grid + cta; if (tile < nfull) issue(s, tile); }
+  }
+  __syncthreads();
+
+  if (wrp == SG_THREADS / 32) {
+    // ---------------- the ninth warp: block-level scan, descriptors, look-back, loads ----------------
+    for (int it = 0;; ++it) {
+      const int tile = it * grid + cta;
+      if (tile >= nfull) break;
+      const int s = it % SP_STAGES, slot = it & 1;
+      unsigned long long lm = 2ull, lxb = 0ull;
+      sp_mbar_wait(bar_agg + 8 * slot, (unsigned)(it >> 1) & 1u);
+      bool f = true; A x = A(0);
+      if (lane < SG_THREADS / 32) { f = s_aggf[slot * 8 + lane] != 0u; x = scan_unbits<A>(s_aggx[slot * 8 + lane]); }
+      bool fi = f; A xi = x;                                             // inclusive over warps 0 .. lane
+#pragma unroll
+      for (int o = 1; o < SG_THREADS / 32; o <<= 1) {
+        const bool ft = __shfl_up_sync(0xffffffffu, (int)fi, o);
+        const A xt = __shfl_up_sync(0xffffffffu, xi, o);
+        if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
+      }
+      const bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); const A xe = __shfl_up_sync(0xffffffffu, xi, 1);
+      const bool agg_f = __shfl_sync(0xffffffffu, (int)fi, SG_THREADS / 32 - 1); const A agg_x = __shfl_sync(0xffffffffu, xi, SG_THREADS / 32 - 1);
+      if (lane == 0) {
+        if (gpu_scope) desc_store_gpu(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+        else desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+      }
+      if (tile - 1 - lane >= 0) { if (gpu_scope) desc_load_gpu(desc + 2 * (long long)(tile - 1 - lane), lm, lxb); else desc_load(desc + 2 * (long long)(tile - 1 - lane), lm, lxb); }
+      if (lane == 0) {
+        const int next = (it + SP_STAGES) * grid + cta;                  // every reader of stage s has arrived
+        if (next < nfull) issue(s, next);
+      }
+      A c = A(0);
+      const bool have_c = tile > 0;
+      if (have_c) {
+        c = chain_lookback_pre<A, OP>(desc, tile, lane, lm, lxb, sleep_ns, gpu_scope);
+        if (lane == 0) {
+          const unsigned long long incl = scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x));
+          if (gpu_scope) desc_store_gpu(desc + 2 * (long long)tile, 2ull | 0x100ull, incl); else desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, incl);
+        }
+      }
+      if (lane < SG_THREADS / 32) {                                      // warp `lane`: exclusive prefix inside the tile, carry included
+        bool have = false; A e = A(0);
+        if (lane > 0) { e = xe; have = true; if (have_c && !fe) e = ScanOp<A, OP>::apply(c, xe); }
+        else if (have_c) { e = c; have = true; }
+        s_prex[slot * 8 + lane] = scan_bits<A>(e);
+        s_preh[slot * 8 + lane] = have ? 1u : 0u;
+      }
+      __syncwarp();
+      if (lane == 0) sp_mbar_arrive(bar_pre + 8 * slot);
+    }
+    return;
+  }
+
+  // ---------------- data warps ----------------
+  bool owe = false; int tp = 0;
+  A xp[SG_ITEMS]; unsigned hmask_p = 0; bool fe_p = false; A xe_p = A(0);
+  int4* my_out = s_out + wrp * 128;
+  auto settle = [&](int itp) {                                           // finish tile tp (iteration itp): prefix, results, store
+    const int slot = itp & 1;
+    sp_mbar_wait(bar_pre + 8 * slot, (unsigned)(itp >> 1) & 1u);
+    const bool have_e = s_preh[slot * 8 + wrp] != 0u; const A e = scan_unbits<A>(s_prex[slot * 8 + wrp]);
+    bool have = false; A pre = A(0);
+    if (lane > 0) { pre = xe_p; have = true; if (have_e && !fe_p) pre = ScanOp<A, OP>::apply(e, xe_p); }
+    else if (have_e) { pre = e; have = true; }
+    const int nopen = !have ? 0 : (hmask_p ? __ffs((int)hmask_p) - 1 : SG_ITEMS);
+    unsigned long long ob[SG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) {
+      const A r = k < nopen ? ScanOp<A, OP>::apply(pre, xp[k]) : xp[k];
+      ob[k] = (std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : (unsigned long long)(long long)r) ^ keyflip;
+    }
+    if (lane == 0) sp_store_read_done();                                 // this warp's previous store has read its slice
+    __syncwarp();
+    sp_write8(s_out, t, ob);
+    sp_fence_async();
+    __syncwarp();
+    if (lane == 0) sp_tensor_store(&tm_out32, tp * SG_THREADS + wrp * 32, sp_saddr(my_out));
+  };
+  int it = 0;
+  for (;; ++it) {
+    const int tile = it * grid + cta;
+    if (tile >= nfull) break;
+    const int s = it % SP_STAGES, slot = it & 1;
+    sp_mbar_wait(bar_full + 8 * s, (unsigned)(it / SP_STAGES) & 1u);
+    unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
+    sp_read8(s_in + (2 * s) * (SG_TILE / 2), t, gl);
+    sp_read8(s_in + (2 * s + 1) * (SG_TILE / 2), t, raw);
+    const long long base = (long long)tile * SG_TILE + (long long)t * SG_ITEMS;
+    long long prev = 0;
+    const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
+    if (lane > 0) prev = left;
+    else if (t > 0) { const int4 q = (s_in + (2 * s) * (SG_TILE / 2))[4 * (t - 1) + (3 ^ (((t - 1) >> 1) & 3))]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
+    else if (tile > 0) { const int4 q = s_left[s]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
+    A x[SG_ITEMS]; unsigned hmask = 0;
+    A tx = A(0); bool uns = false, bad = false;
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) {
+      const long long g = (long long)gl[k];
+      const bool head = (k == 0 && base == 0) || g != prev;
+      uns |= g < prev && !(k == 0 && base == 0);
+      bad |= (unsigned long long)g >= (unsigned long long)p.size;
+      prev = g;
+      A v;
+      if (VK == 2) { double d = __longlong_as_double((long long)raw[k]); if (NANSKIP && d != d) d = OP == SC_SUM ? 0.0 : 1.0; v = (A)d; }
+      else v = (A)(long long)(raw[k] ^ keyflip);
+      tx = (k == 0 || head) ? v : ScanOp<A, OP>::apply(tx, v);
+      hmask |= head ? (1u << k) : 0u;
+      x[k] = tx;
+    }
+    if (uns) *p.unsorted_w = 1;
+    if (bad) p.status[AGC_ST_BADLABEL] = 1;
+    bool fi = hmask != 0u; A xi = tx;                                    // inclusive over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const bool ft = __shfl_up_sync(0xffffffffu, (int)fi, o);
+      const A xt = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
+    }
+    const bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); const A xe = __shfl_up_sync(0xffffffffu, xi, 1);
+    if (lane == 31) {                                                    // (every lane of the warp is past its reads of stage s)
+      s_aggf[slot * 8 + wrp] = fi ? 1u : 0u; s_aggx[slot * 8 + wrp] = scan_bits<A>(xi);
+      sp_mbar_arrive(bar_agg + 8 * slot);
+    }
+    if (owe) settle(it - 1);
+#pragma unroll
+    for (int k = 0; k < SG_ITEMS; ++k) xp[k] = x[k];
+    hmask_p = hmask; fe_p = fe; xe_p = xe; tp = tile; owe = true;
+  }
+  if (owe) settle(it - 1);
+  if (lane == 0) sp_store_done();
 }
 
 // single block: segmented scan over the tile aggregates -> carry for tile t = aggregate of tiles [0, t).
@@ -1375,12 +1571,12 @@ inline sp_encode_fn sp_encoder() {
   }();
   return fn;
 }
-inline bool sp_tile_map(CUtensorMap* tm, const void* base, int nfull) {
+inline bool sp_tile_map(CUtensorMap* tm, const void* base, int nfull, int box_rows = SG_THREADS) {
   sp_encode_fn enc = sp_encoder();
   if (!enc || nfull <= 0) return false;
   const cuuint64_t dims[2] = {8, (cuuint64_t)nfull * SG_THREADS};
   const cuuint64_t strides[1] = {64};
-  const cuuint32_t box[2] = {8, SG_THREADS}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {8, (cuuint32_t)box_rows}, estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1417,8 +1613,14 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
           const bool pipe_on = pipe_env && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo, p.out, nfull);
           if (warp_on && !pipe_on) cudaMemsetAsync(dw, 0, (size_t)nfull * (SG_THREADS / 32) * 16, st);
           const int pgrid = nfull < 2 * device_sms() ? nfull : 2 * device_sms();
+          static const bool ws_on = !(getenv("AGC_SCAN_WS") && atoi(getenv("AGC_SCAN_WS")) == 0);
+          CUtensorMap tmo32;                                     // one warp's 32 rows of the result
+          const bool ws_ok = pipe_on && ws_on && sp_tile_map(&tmo32, p.out, nfull, 32);
 #define AGC_PIPE(VK_, NS_)                                                                                              \
-          { static std::atomic<unsigned long long> attr_done{0};                                                           \
+          if (ws_ok) { static std::atomic<unsigned long long> attr_done{0};                                                \
+            ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_>, WS_SMEM, attr_done);                                           \
+            k_seg_scan_ws<A, OP, VK_, NS_><<<pgrid, WS_THREADS, WS_SMEM, st>>>(p, d, nfull, tml, tmv, tmo32); }            \
+          else { static std::atomic<unsigned long long> attr_done{0};                                                      \
             ensure_dyn_smem(k_seg_scan_pipe<A, OP, VK_, NS_>, SP_SMEM, attr_done);                                         \
             k_seg_scan_pipe<A, OP, VK_, NS_><<<pgrid, SG_THREADS, SP_SMEM, st>>>(p, d, nfull, tml, tmv, tmo); }
 #define AGC_LEAN(VK_, NS_)                                                                                              \
@@ -1479,7 +1681,7 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
   p.fill_f = r->fill_f64; p.fill_i = r->fill_i64;
   p.a_float = dtype_is_float(r->a_dtype); p.a_u64 = r->a_dtype == AGC_DT_U64;
   p.labels = r->index.labels; p.size = r->size; p.status = r->status;
-  { static const int lb_sleep = getenv("AGC_LB_SLEEP") ? atoi(getenv("AGC_LB_SLEEP")) : 0; p.lb_sleep = lb_sleep; }
+  { static const int lb_sleep = (getenv("AGC_LB_SLEEP") ? atoi(getenv("AGC_LB_SLEEP")) & 0xffff : 0) | ((getenv("AGC_DESC_GPU") && atoi(getenv("AGC_DESC_GPU"))) ? (1 << 30) : 0); p.lb_sleep = lb_sleep; }
 
   // ---- flat int32/int64 labels: try the direct (already sorted) scan first -------------------------------
   int direct_lt = 0;

@@ -133,6 +133,96 @@ __global__ void __launch_bounds__(1024, 1) k_spill1(const long long* __restrict_
   if (threadIdx.x == 0) rcount[blockIdx.x] = s_fill;
   for (int i = threadIdx.x; i < cov; i += blockDim.x) if (su[i]) red_f64(tab + i, (double)su[i]);
 }
+// same as k_spill1 with the next vector's loads in flight while the current one is compacted (ballot ranks, one
+// shared-memory atomic per warp and vector, stores contiguous across the lanes)
+__global__ void __launch_bounds__(1024, 1) k_spill1b(const long long* __restrict__ idx, const float* __restrict__ a, long long n,
+                                                     double* tab, int cov, unsigned short* rslot, float* rval, unsigned* rcount, long long cap) {
+  extern __shared__ unsigned su[];
+  __shared__ unsigned s_fill;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i = threadIdx.x; i < cov; i += blockDim.x) su[i] = 0u;
+  if (threadIdx.x == 0) s_fill = 0u;
+  __syncthreads();
+  unsigned short* myslot = rslot + (long long)blockIdx.x * cap;
+  float* myval = rval + (long long)blockIdx.x * cap;
+  const long long nvec = n >> 2, per = (nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * per, v1 = v0 + per < nvec ? v0 + per : nvec;
+  int4 l0 = make_int4(0, 0, 0, 0), l1 = l0, av = l0;
+  long long v = v0 + threadIdx.x;
+  if (v < v1) {
+    l0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v);
+    l1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v + 1);
+    av = ldg_stream(reinterpret_cast<const int4*>(a) + v);
+  }
+  for (long long vb = v0; vb < v1; vb += blockDim.x) {
+    const bool live = v < v1;
+    const long long vn = v + blockDim.x;
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = n0, na = n0;
+    if (vn < v1) {
+      n0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * vn);
+      n1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * vn + 1);
+      na = ldg_stream(reinterpret_cast<const int4*>(a) + vn);
+    }
+    const int g4[4] = {l0.x, l0.z, l1.x, l1.z};
+    const int x4[4] = {av.x, av.y, av.z, av.w};
+    unsigned m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool unc = live && g4[j] >= cov;
+      m[j] = __ballot_sync(0xffffffffu, unc);
+      if (live && g4[j] < cov) atomicAdd(&su[g4[j]], (unsigned)x4[j] >> 20);
+    }
+    const unsigned c0 = __popc(m[0]), c1 = __popc(m[1]), c2 = __popc(m[2]), c3 = __popc(m[3]);
+    unsigned base = 0;
+    if (lane == 0 && (c0 + c1 + c2 + c3)) base = atomicAdd(&s_fill, c0 + c1 + c2 + c3);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned off[4] = {base, base + c0, base + c0 + c1, base + c0 + c1 + c2};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (m[j] >> lane & 1u) { const unsigned q = off[j] + __popc(m[j] & lt); myslot[q] = (unsigned short)(g4[j] - cov); myval[q] = __int_as_float(x4[j]); }
+    l0 = n0; l1 = n1; av = na; v = vn;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) rcount[blockIdx.x] = s_fill;
+  for (int i = threadIdx.x; i < cov; i += blockDim.x) if (su[i]) red_f64(tab + i, (double)su[i]);
+}
+// the RED variant with the same skeleton (prefetched loads), for a like-for-like comparison
+__global__ void __launch_bounds__(1024, 1) k_red1b(const long long* __restrict__ idx, const float* __restrict__ a, long long n, double* tab, int cov) {
+  extern __shared__ unsigned su[];
+  for (int i = threadIdx.x; i < cov; i += blockDim.x) su[i] = 0u;
+  __syncthreads();
+  const long long nvec = n >> 2, per = (nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * per, v1 = v0 + per < nvec ? v0 + per : nvec;
+  int4 l0 = make_int4(0, 0, 0, 0), l1 = l0, av = l0;
+  long long v = v0 + threadIdx.x;
+  if (v < v1) {
+    l0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v);
+    l1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v + 1);
+    av = ldg_stream(reinterpret_cast<const int4*>(a) + v);
+  }
+  for (long long vb = v0; vb < v1; vb += blockDim.x) {
+    const bool live = v < v1;
+    const long long vn = v + blockDim.x;
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = n0, na = n0;
+    if (vn < v1) {
+      n0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * vn);
+      n1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * vn + 1);
+      na = ldg_stream(reinterpret_cast<const int4*>(a) + vn);
+    }
+    const int g4[4] = {l0.x, l0.z, l1.x, l1.z};
+    const int x4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!live) continue;
+      if (g4[j] < cov) atomicAdd(&su[g4[j]], (unsigned)x4[j] >> 20);
+      else red_f64(tab + g4[j], (double)__int_as_float(x4[j]));
+    }
+    l0 = n0; l1 = n1; av = na; v = vn;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cov; i += blockDim.x) if (su[i]) red_f64(tab + i, (double)su[i]);
+}
 __global__ void __launch_bounds__(1024, 1) k_spill2(const unsigned short* __restrict__ rslot, const float* __restrict__ rval,
                                                     const unsigned* __restrict__ rcount, long long cap, double* tab, int cov, int G) {
   extern __shared__ unsigned su[];
@@ -214,8 +304,8 @@ int main(int argc, char** argv) {
     }
   }
   {
-    CK(cudaFuncSetAttribute((const void*)k_spill1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    CK(cudaFuncSetAttribute((const void*)k_spill2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    CK(cudaFuncSetAttribute((const void*)k_spill1, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX - 1024));
+    CK(cudaFuncSetAttribute((const void*)k_spill2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX - 1024));
     const int cov = 199552 / 4;                                   // 49 888 groups in the table, the rest spilled
     const long long cap = ((N / sms) * 3 / 4 + 63) / 64 * 64;     // records per CTA region (50 % expected)
     unsigned short* rslot; float* rval; unsigned* rcount;
@@ -225,6 +315,11 @@ int main(int argc, char** argv) {
     double ms2 = time_ms([&] { k_spill2<<<sms, 1024, 227 * 1024 - 1024>>>(rslot, rval, rcount, cap, tab, cov, (int)G); });
     double both = time_ms([&] { k_spill1<<<sms, 1024, 199552>>>(idx, a, N, tab, cov, rslot, rval, rcount, cap);
                                 k_spill2<<<sms, 1024, 227 * 1024 - 1024>>>(rslot, rval, rcount, cap, tab, cov, (int)G); });
+    CK(cudaFuncSetAttribute((const void*)k_spill1b, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX - 1024));
+    CK(cudaFuncSetAttribute((const void*)k_red1b, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX - 1024));
+    double ms1b = time_ms([&] { k_spill1b<<<sms, 1024, 199552>>>(idx, a, N, tab, cov, rslot, rval, rcount, cap); });
+    double msr = time_ms([&] { k_red1b<<<sms, 1024, 199552>>>(idx, a, N, tab, cov); });
+    printf("{\"mode\": \"prefetched skeleton\", \"spill_pass1_ms\": %.3f, \"atoms_red_ms\": %.3f}\n", ms1b, msr);
     printf("{\"mode\": \"atoms + spilled records (u16 slot, f32), replay kernel\", \"cov\": %d, \"pass1_ms\": %.3f, \"pass2_ms\": %.3f, \"both_ms\": %.3f, \"gelem_s\": %.1f}\n",
            cov, ms1, ms2, both, N / both * 1e-6);
   }
