@@ -517,7 +517,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            ne = min(n, 1 << 28)
+            ne = n if world == 1 else min(n, 1 << 28)        # one GPU: the full workload; under torchrun 2^28 per rank (8 ranks share one host)
             hl_t, ha_t = labels[:ne].cpu().pin_memory(), a[:ne].cpu().pin_memory()
             hl, ha = hl_t.numpy(), ha_t.numpy()               # numpy views of the pinned buffers
 

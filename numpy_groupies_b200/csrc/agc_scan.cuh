@@ -845,126 +845,9 @@ __global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_lean(const ScanPar
   warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_seg_scan_warp: the chained scan with the WARP as the chained unit.  ncu on k_seg_scan_lean (r2j): half of all warp
-// time is spent at the CTA barriers -- seven warps wait for the slowest warp's loads, then all eight wait for warp 0's
-// look-back -- and a tile lives 8 us of which its loads are in flight for 2.5.  Here every warp owns a 256-element tile
-// with its own descriptor: it loads, scans with shuffles, publishes, looks back over the 32 warp tiles before it and
-// stores, without ever meeting another warp at a barrier.  Warp tiles are numbered blockIdx * 8 + warp, CTAs start in
-// blockIdx order and all warps of a CTA are resident together, so every descriptor a warp waits for belongs to a warp
-// that is running or done.  The last warp of a CTA also publishes the CTA-level descriptor the tail kernel
-// (k_seg_scan_direct<.., 2>, the ragged last tile) looks back at.
-// ---------------------------------------------------------------------------------------------
-template <class A, int OP>
-__device__ __forceinline__ A chain_lookback_near(const unsigned long long* desc, int t, int lane, unsigned sleep_ns) {
-  A acc = A(0); bool have = false;
-  int look = t - 1 - lane;
-  for (;;) {
-    unsigned long long m = 2ull, xb = 0ull;                    // tiles before tile 0 never matter
-    if (look >= 0) desc_load(desc + 2 * (long long)look, m, xb);
-    int first;
-    for (;;) {                                                 // wait only for the descriptors up to the nearest terminator seen so far
-      const bool pub = (m & 3ull) != 0ull;
-      const bool term = pub && ((m & 3ull) == 2ull || (m & 0x100ull) != 0ull);
-      const unsigned pb = __ballot_sync(0xffffffffu, pub), tb = __ballot_sync(0xffffffffu, term);
-      first = tb ? __ffs((int)tb) - 1 : 32;
-      const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
-      if ((pb & need) == need) break;
-      if (!pub && lane <= first) {
-        if (sleep_ns) __nanosleep(sleep_ns);
-        desc_load(desc + 2 * (long long)look, m, xb);
-      }
-    }
-    A x = scan_unbits<A>(xb);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {                         // lane i ends with the fold of lanes [i, first], farthest first
-      const A y = __shfl_down_sync(0xffffffffu, x, o);
-      if (lane + o <= first && lane + o < 32) x = ScanOp<A, OP>::apply(y, x);
-    }
-    const A win = __shfl_sync(0xffffffffu, x, 0);
-    acc = have ? ScanOp<A, OP>::apply(win, acc) : win; have = true;
-    if (first < 32) break;
-    look -= 32;
-  }
-  return acc;
-}
-
-template <class A, int OP, int VK, bool NANSKIP, int OCC>
-__global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_warp(const ScanParams p, unsigned long long* desc_cta, unsigned long long* desc) {
-  __shared__ int4 s_stage[SG_THREADS / 32][128];
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int wt = (int)blockIdx.x * (SG_THREADS / 32) + wrp;      // this warp's tile
-  if (*(volatile const int*)p.unsorted) {                        // somebody found an inversion: the sort-based path redoes everything
-    if (lane == 0) {
-      desc_store(desc + 2 * (long long)wt, 2ull | 0x100ull, 0ull);
-      if (wrp == SG_THREADS / 32 - 1) desc_store(desc_cta + 2 * (long long)blockIdx.x, 2ull | 0x100ull, 0ull);
-    }
-    return;
-  }
-  const long long wbase = (long long)wt * (32 * SG_ITEMS);
-  const long long base = wbase + (long long)lane * SG_ITEMS;
-  int4 raw_lab[4], raw_val[4];
-  warp_fetch8((const long long*)p.labels + wbase, lane, raw_lab);
-  warp_fetch8((const unsigned long long*)p.a + wbase, lane, raw_val);
-  long long prev0 = 0;
-  if (lane == 0 && wbase > 0) prev0 = ((const long long*)p.labels)[wbase - 1];
-  unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
-  warp_transpose8(raw_lab, s_stage[wrp], lane, gl);
-  warp_transpose8(raw_val, s_stage[wrp], lane, raw);
-  const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
-  long long prev = lane > 0 ? left : prev0;
-  A x[SG_ITEMS]; unsigned hmask = 0;                           // bit k: element k opens a segment
-  A tx = A(0); bool uns = false, bad = false;
-  const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
-#pragma unroll
-  for (int k = 0; k < SG_ITEMS; ++k) {
-    const long long g = (long long)gl[k];
-    const bool head = (k == 0 && base == 0) || g != prev;
-    uns |= g < prev && !(k == 0 && base == 0);
-    bad |= (unsigned long long)g >= (unsigned long long)p.size;
-    prev = g;
-    A v;
-    if (VK == 2) { double d = __longlong_as_double((long long)raw[k]); if (NANSKIP && d != d) d = OP == SC_SUM ? 0.0 : 1.0; v = (A)d; }
-    else v = (A)(long long)(raw[k] ^ keyflip);                 // int64 as is; uint64 max / min: order-preserving key
-    tx = (k == 0 || head) ? v : ScanOp<A, OP>::apply(tx, v);
-    hmask |= head ? (1u << k) : 0u;
-    x[k] = tx;                                                 // thread-local inclusive scan
-  }
-  if (uns) *p.unsorted_w = 1;
-  if (bad) p.status[AGC_ST_BADLABEL] = 1;
-  // inclusive segmented scan of the 32 thread aggregates
-  bool fi = hmask != 0u; A xi = tx;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const bool ft = __shfl_up_sync(0xffffffffu, (int)fi, o);
-    const A xt = __shfl_up_sync(0xffffffffu, xi, o);
-    if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
-  }
-  const bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); const A xe = __shfl_up_sync(0xffffffffu, xi, 1);
-  const bool agg_f = __shfl_sync(0xffffffffu, (int)fi, 31); const A agg_x = __shfl_sync(0xffffffffu, xi, 31);
-  if (lane == 0) desc_store(desc + 2 * (long long)wt, (wt == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
-  A c = A(0);
-  if (wt > 0) c = chain_lookback_near<A, OP>(desc, wt, lane, (unsigned)p.lb_sleep & 0xffffu);
-  if (lane == 0) {
-    const unsigned long long incl = scan_bits<A>((agg_f || wt == 0) ? agg_x : ScanOp<A, OP>::apply(c, agg_x));
-    if (wt > 0) desc_store(desc + 2 * (long long)wt, 2ull | 0x100ull, incl);
-    if (wrp == SG_THREADS / 32 - 1) desc_store(desc_cta + 2 * (long long)blockIdx.x, 2ull | 0x100ull, incl);
-  }
-  const bool have_c = wt > 0;
-  bool have = false; A pre = A(0);
-  if (lane > 0) { pre = xe; have = true; if (have_c && !fe) pre = ScanOp<A, OP>::apply(c, xe); }
-  else if (have_c) { pre = c; have = true; }
-  // the prefix applies to the elements before this thread's first segment head
-  const int nopen = !have ? 0 : (hmask ? __ffs((int)hmask) - 1 : SG_ITEMS);
-  unsigned long long ob[SG_ITEMS];
-#pragma unroll
-  for (int k = 0; k < SG_ITEMS; ++k) {
-    const A r = k < nopen ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
-    ob[k] = (std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : (unsigned long long)(long long)r) ^ keyflip;
-  }
-  warp_store_blocked8((A*)p.out + wbase, s_stage[wrp], lane, ob);
-}
-
+// (Measured and removed: the same kernel with the WARP as the chained unit -- a 256-element tile and a descriptor per warp, no
+//  CTA barrier at all.  1.68 ms at 5 CTAs per SM, 1.76 at 6, against 1.55 here: eight times the descriptors, a dependent global
+//  load for the label left of every warp tile, and the duty cycle of the loads no better.  profiles/r02i_scan_variants.jsonl)
 // ---------------------------------------------------------------------------------------------
 // k_seg_scan_pipe: the chained scan as a PERSISTENT kernel fed by the TMA.  What the one-tile-per-CTA kernels above cannot
 // fix is their duty cycle: a tile has its loads in flight for ~2.5 us of an 8 us life, and even the plain two-pass kernels
@@ -1511,7 +1394,7 @@ inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   w.hist = take(256ll * nb * 4); w.tsum = take((xs_tiles(256ll * nb) + 1) * 4);
   const long long ntiles = (n + SG_TILE - 1) / SG_TILE + 1;
   w.tile_f = take(ntiles); w.tile_x = take(ntiles * 8); w.carry_f = take(ntiles); w.carry_x = take(ntiles * 8);
-  w.desc = take(ntiles * 16 * (1 + SG_THREADS / 32));     // CTA-level descriptors, then one per warp tile (k_seg_scan_warp)
+  w.desc = take(ntiles * 16);
   w.flag = take(256);
   w.total = o;
   return w;
@@ -1603,31 +1486,31 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
           unsigned long long* d = (unsigned long long*)(ws + L.desc);
           const bool ns = (p.flags & AGC_F_NANSKIP) != 0;
           AGC_COUNT_LAUNCH(1);
-          // resident CTAs per SM (register budget 65536 / (256 * OCC)): the kernel is bound by loads in flight, more CTAs win
-          // until the spills bite (k_seg_scan_lean at N = 2^28, cumsum: 5 CTAs / 48 registers 1.66 ms, 6 / 40 1.55 ms)
+          // AGC_SCAN_PIPE=0: the one-tile-per-CTA kernel (k_seg_scan_lean); AGC_SCAN_WS=0: the persistent kernel with CTA barriers
           static const int occ = getenv("AGC_SCAN_OCC") ? atoi(getenv("AGC_SCAN_OCC")) : 6;
-          static const bool warp_on = getenv("AGC_SCAN_WARP") && atoi(getenv("AGC_SCAN_WARP")) != 0;   // measured: 1.68 ms against 1.55 for the CTA-tile kernel
-          unsigned long long* dw = d + 2 * (long long)ntiles;    // warp-tile descriptors
           static const bool pipe_env = !(getenv("AGC_SCAN_PIPE") && atoi(getenv("AGC_SCAN_PIPE")) == 0);
-          CUtensorMap tml, tmv, tmo;                             // 256 rows x 64 bytes per tile, 64-byte swizzle
-          const bool pipe_on = pipe_env && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo, p.out, nfull);
-          if (warp_on && !pipe_on) cudaMemsetAsync(dw, 0, (size_t)nfull * (SG_THREADS / 32) * 16, st);
-          const int pgrid = nfull < 2 * device_sms() ? nfull : 2 * device_sms();
           static const bool ws_on = !(getenv("AGC_SCAN_WS") && atoi(getenv("AGC_SCAN_WS")) == 0);
-          CUtensorMap tmo32;                                     // one warp's 32 rows of the result
+          CUtensorMap tml, tmv, tmo, tmo32;                      // tiles of 256 rows x 64 bytes (64-byte swizzle); tmo32: one warp's 32 rows of the result
+          const bool pipe_on = pipe_env && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo, p.out, nfull);
           const bool ws_ok = pipe_on && ws_on && sp_tile_map(&tmo32, p.out, nfull, 32);
+          // the persistent kernels walk the tiles round robin and wait for their neighbours: every CTA of the grid must be
+          // resident, so the grid is what the occupancy calculator grants (two CTAs per SM), never more
 #define AGC_PIPE(VK_, NS_)                                                                                              \
-          if (ws_ok) { static std::atomic<unsigned long long> attr_done{0};                                                \
-            ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_>, WS_SMEM, attr_done);                                           \
-            k_seg_scan_ws<A, OP, VK_, NS_><<<pgrid, WS_THREADS, WS_SMEM, st>>>(p, d, nfull, tml, tmv, tmo32); }            \
-          else { static std::atomic<unsigned long long> attr_done{0};                                                      \
-            ensure_dyn_smem(k_seg_scan_pipe<A, OP, VK_, NS_>, SP_SMEM, attr_done);                                         \
-            k_seg_scan_pipe<A, OP, VK_, NS_><<<pgrid, SG_THREADS, SP_SMEM, st>>>(p, d, nfull, tml, tmv, tmo); }
+          { static std::atomic<unsigned long long> attr_done{0};                                                           \
+            int per_sm = 0;                                                                                                \
+            if (ws_ok) { ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_>, WS_SMEM, attr_done);                              \
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_ws<A, OP, VK_, NS_>, WS_THREADS, WS_SMEM); } \
+            else { ensure_dyn_smem(k_seg_scan_pipe<A, OP, VK_, NS_>, SP_SMEM, attr_done);                                  \
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_pipe<A, OP, VK_, NS_>, SG_THREADS, SP_SMEM); } \
+            const long long cap = (long long)per_sm * device_sms();                                                        \
+            const int pgrid = (int)(nfull < cap ? nfull : cap);                                                            \
+            if (pgrid <= 0) launched = false;                                                                              \
+            else if (ws_ok) k_seg_scan_ws<A, OP, VK_, NS_><<<pgrid, WS_THREADS, WS_SMEM, st>>>(p, d, nfull, tml, tmv, tmo32); \
+            else k_seg_scan_pipe<A, OP, VK_, NS_><<<pgrid, SG_THREADS, SP_SMEM, st>>>(p, d, nfull, tml, tmv, tmo); }
 #define AGC_LEAN(VK_, NS_)                                                                                              \
-          { if (pipe_on) AGC_PIPE(VK_, NS_)                                                                                \
-            else if (warp_on) {                                                                                            \
-              if (occ == 5) k_seg_scan_warp<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d, dw);                    \
-              else k_seg_scan_warp<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d, dw); }                           \
+          { bool launched = pipe_on;                                                                                       \
+            if (pipe_on) AGC_PIPE(VK_, NS_)                                                                                \
+            if (launched) {}                                                                                               \
             else if (occ == 5) k_seg_scan_lean<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
             else k_seg_scan_lean<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d); }
           if (flts) { if (ns) AGC_LEAN(2, true) else AGC_LEAN(2, false) }
