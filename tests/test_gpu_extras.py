@@ -313,3 +313,31 @@ def test_fused_min_max_shared_memory_kernel(groups):
             assert torch.equal(res[f].view(torch.int32), one.view(torch.int32)), f
             with np.errstate(all="ignore"):
                 np.testing.assert_array_equal(res[f].cpu().numpy(), oracle.aggregate(g, a, func=f, size=groups, fill_value=-7))
+
+
+@pytest.mark.parametrize("func", ["sum", "max", "len", "mean", "cumsum", "first"])
+def test_pageable_int64_labels_are_narrowed_on_the_way_to_the_device(func, monkeypatch):
+    """Host-array path: pageable int64 / uint64 labels of a Form 1 call with a known size cross PCIe as int32 (narrowed by the
+    staging threads, agc_host_narrow_labels).  Same results as the plain upload, and labels the narrowing cannot represent
+    are still reported as bad labels -- negative, >= size, >= 2^31."""
+    rng = np.random.default_rng(11)
+    n, groups = (1 << 21) + 13, 70001                        # 16 MB of int64 labels: above the staging threshold
+    gidx = rng.integers(0, groups, n)
+    a = rng.random(n).astype(np.float32) if func != "cumsum" else rng.integers(-1000, 1000, n)
+    got = aggregate(gidx, a, func=func, size=groups)
+    monkeypatch.setattr(ac, "_NARROW_LABELS", False)
+    plain = aggregate(gidx, a, func=func, size=groups)
+    monkeypatch.setattr(ac, "_NARROW_LABELS", True)
+    assert got.dtype == plain.dtype
+    if func in ("sum", "mean"):
+        np.testing.assert_allclose(got, plain, rtol=1e-6)
+        np.testing.assert_allclose(got, oracle.aggregate(gidx, a, func=func, size=groups), rtol=1e-5)
+    else:
+        np.testing.assert_array_equal(got, plain)
+        np.testing.assert_array_equal(got, oracle.aggregate(gidx, a, func=func, size=groups))
+    np.testing.assert_array_equal(aggregate(gidx.astype(np.uint64), a, func=func, size=groups), got)
+    for bad in (-1, groups, 2**31, 2**31 + 5, -2**40):
+        g2 = gidx.copy()
+        g2[n // 3] = bad
+        with pytest.raises(ValueError):
+            aggregate(g2, a, func=func, size=groups)
