@@ -849,24 +849,19 @@ __global__ void __launch_bounds__(SG_THREADS, OCC) k_seg_scan_lean(const ScanPar
 //  CTA barrier at all.  1.68 ms at 5 CTAs per SM, 1.76 at 6, against 1.55 here: eight times the descriptors, a dependent global
 //  load for the label left of every warp tile, and the duty cycle of the loads no better.  profiles/r02i_scan_variants.jsonl)
 // ---------------------------------------------------------------------------------------------
-// k_seg_scan_pipe: the chained scan as a PERSISTENT kernel fed by the TMA.  What the one-tile-per-CTA kernels above cannot
-// fix is their duty cycle: a tile has its loads in flight for ~2.5 us of an 8 us life, and even the plain two-pass kernels
-// (no chain at all) stream at 4.5-5.3 TB/s.  Here a CTA of 256 threads walks the tiles round robin with the rest of the grid
-// (all CTAs are resident, so every tile a look-back waits for is being worked on), and its thread 0 keeps
-// the loads of the next SP_STAGES - 1 tiles in flight with cp.async.bulk into a ring in shared memory (complete_tx on one
-// mbarrier per stage: 16 KB of labels, 16 KB of values, and the 16 bytes before the tile for the label left of it) -- the
-// bytes in flight no longer depend on what the threads are doing.  The threads read their 8 consecutive elements from the
-// linear buffers in a rotated order (unit (k + t/2) % 4 at step k: conflict-free 128-bit accesses) and rotate the
-// registers back.  The look-back is software-pipelined: a tile publishes its aggregate as soon as its block scan is done,
-// but its own look-back runs one iteration later -- the descriptor loads are issued before the next tile's data is touched
-// and by then every predecessor has published -- so no thread ever waits for the chain.  Results leave through a 16 KB
-// buffer with one bulk store per tile.  3 stages * 32 KB + 16 KB = 112 KB per CTA, two CTAs per SM.
+// The chained scan as a PERSISTENT kernel fed by the TMA (k_seg_scan_ws below; these are its building blocks).  What the
+// one-tile-per-CTA kernels above cannot fix is their duty cycle: a tile has its loads in flight for ~2.5 us of an 8 us life,
+// and even the plain two-pass kernels (no chain at all) stream at 4.5-5.3 TB/s.  A persistent CTA keeps the loads of the next
+// SP_STAGES tiles in flight with cp.async.bulk.tensor into a ring in shared memory (complete_tx on one mbarrier per stage:
+// 16 KB of labels, 16 KB of values, and the 16 bytes before the tile for the label left of it) -- the bytes in flight no longer
+// depend on what the threads are doing -- and the results leave through shared memory with bulk tensor stores.
+// 3 stages * 32 KB + 16 KB of results = 112 KB per CTA, two CTAs per SM.
+// (History, profiles/r02i_scan_variants.jsonl: the first persistent kernel kept the CTA-wide structure -- block scan behind two
+//  barriers, warp 0's look-back with seven warps waiting, one 16 KB store per tile: cumsum 1.28 ms, cummax 1.43-1.57;
+//  k_seg_scan_ws replaced it.)
 // ---------------------------------------------------------------------------------------------
 constexpr int SP_STAGES = 3;
 constexpr int SP_IN_BYTES = SG_TILE * 8;                         // one array of one tile
-// 7 tile buffers (3 stages of labels + values, one for the results) at a 512-byte aligned address, then the mbarriers and
-// the "label left of the tile" slots
-constexpr int SP_SMEM = (2 * SP_STAGES + 1) * SP_IN_BYTES + 512 + SP_STAGES * 16 + 64;
 __device__ __forceinline__ unsigned sp_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sp_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void sp_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
@@ -950,130 +945,12 @@ __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, 
   return acc;
 }
 
-template <class A, int OP, int VK, bool NANSKIP>
-__global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_pipe(const ScanParams p, unsigned long long* desc, int nfull,
-                                                                 const __grid_constant__ CUtensorMap tm_lab, const __grid_constant__ CUtensorMap tm_val,
-                                                                 const __grid_constant__ CUtensorMap tm_out) {
-  extern __shared__ __align__(16) unsigned char sp_dyn[];          // (a larger alignment here would pad the static shared memory of EVERY kernel in this translation unit)
-  unsigned char* sp_raw = sp_dyn + ((512u - (sp_saddr(sp_dyn) & 511u)) & 511u);      // the swizzle pattern is a function of the address
-  int4* s_in = (int4*)sp_raw;                                            // [stage][labels | values][1024 units]
-  int4* s_out = (int4*)(sp_raw + SP_STAGES * 2 * SP_IN_BYTES);
-  int4* s_left = (int4*)(sp_raw + SP_STAGES * 2 * SP_IN_BYTES + SP_IN_BYTES);   // [stage]: the 16 bytes before the tile's labels
-  unsigned long long* s_bar = (unsigned long long*)(s_left + SP_STAGES);
-  __shared__ unsigned long long s_carry;
-  const int t = threadIdx.x, lane = t & 31;
-  const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
-  // tiles go round robin: iteration `it` of CTA b owns tile it * gridDim + b, so that neighbouring tiles are worked on at
-  // the same time by neighbouring CTAs (with tickets taken at prefetch time CTA 0 held tiles 0, 1, 2 and CTA 1 waited two
-  // iterations for tile 2 before it could finish tile 3, and so on down the grid: a start-up ramp of half the run time).
-  // All CTAs of the grid (two per SM) are resident together, so every tile a look-back waits for is being worked on.
-  const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
-  auto issue = [&](int s, int tile) {                                    // thread 0: the loads of one tile into stage s
-    const unsigned bar = sp_saddr(s_bar + s);
-    sp_expect_tx(bar, 2 * SP_IN_BYTES + (tile > 0 ? 16 : 0));
-    sp_tensor_load(sp_saddr(s_in + (2 * s) * (SG_TILE / 2)), &tm_lab, tile * SG_THREADS, bar);
-    sp_tensor_load(sp_saddr(s_in + (2 * s + 1) * (SG_TILE / 2)), &tm_val, tile * SG_THREADS, bar);
-    if (tile > 0) sp_bulk_load(sp_saddr(s_left + s), (const long long*)p.labels + (long long)tile * SG_TILE - 2, 16, bar);
-  };
-  if (t == 0) {
-#pragma unroll
-    for (int s = 0; s < SP_STAGES; ++s) sp_mbar_init(sp_saddr(s_bar + s), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sp_fence_async();
-#pragma unroll
-    for (int s = 0; s < SP_STAGES; ++s) { const int tile = s * grid + cta; if (tile < nfull) issue(s, tile); }
-  }
-  __syncthreads();
-  // the tile whose results are still owed (its look-back runs one iteration late)
-  bool owe = false; int tp = 0;
-  A xp[SG_ITEMS]; unsigned hmask_p = 0; bool pf_p = false, have_p_p = false, aggf_p = false; A px_p = A(0), aggx_p = A(0);
-  auto settle = [&](unsigned long long m, unsigned long long xb) {       // finish tile tp: look-back, prefix, results, bulk store
-    if (t < 32) {
-      A c = A(0);
-      if (tp > 0) {
-        c = chain_lookback_pre<A, OP>(desc, tp, lane, m, xb);
-        if (lane == 0) desc_store(desc + 2 * (long long)tp, 2ull | 0x100ull, scan_bits<A>(aggf_p ? aggx_p : ScanOp<A, OP>::apply(c, aggx_p)));
-      }
-      if (lane == 0) { s_carry = scan_bits<A>(c); sp_store_read_done(); }    // the previous bulk store has read s_out
-    }
-    __syncthreads();
-    const bool have_c = tp > 0; const A cx = scan_unbits<A>(s_carry);
-    bool have = false; A pre = A(0);
-    if (have_p_p) { pre = px_p; have = true; if (have_c && !pf_p) pre = ScanOp<A, OP>::apply(cx, px_p); }
-    else if (have_c) { pre = cx; have = true; }
-    const int nopen = !have ? 0 : (hmask_p ? __ffs((int)hmask_p) - 1 : SG_ITEMS);
-    unsigned long long ob[SG_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SG_ITEMS; ++k) {
-      const A r = k < nopen ? ScanOp<A, OP>::apply(pre, xp[k]) : xp[k];
-      ob[k] = (std::is_same<A, double>::value ? (unsigned long long)__double_as_longlong((double)r) : (unsigned long long)(long long)r) ^ keyflip;
-    }
-    sp_write8(s_out, t, ob);
-    sp_fence_async();
-    __syncthreads();
-    if (t == 0) sp_tensor_store(&tm_out, tp * SG_THREADS, sp_saddr(s_out));
-  };
-  for (int it = 0;; ++it) {
-    const int s = it % SP_STAGES;
-    const unsigned parity = (unsigned)(it / SP_STAGES) & 1u;
-    const int tile = it * grid + cta;
-    if (tile >= nfull) break;
-    unsigned long long lm = 2ull, lxb = 0ull;                            // look-back of the owed tile: request its window now
-    if (owe && t < 32 && tp - 1 - lane >= 0) desc_load(desc + 2 * (long long)(tp - 1 - lane), lm, lxb);
-    sp_mbar_wait(sp_saddr(s_bar + s), parity);
-    unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
-    sp_read8(s_in + (2 * s) * (SG_TILE / 2), t, gl);
-    sp_read8(s_in + (2 * s + 1) * (SG_TILE / 2), t, raw);
-    const long long base = (long long)tile * SG_TILE + (long long)t * SG_ITEMS;
-    long long prev = 0;
-    const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
-    if (lane > 0) prev = left;
-    else if (t > 0) { const int4 q = (s_in + (2 * s) * (SG_TILE / 2))[4 * (t - 1) + (3 ^ (((t - 1) >> 1) & 3))]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
-    else if (tile > 0) { const int4 q = s_left[s]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
-    A x[SG_ITEMS]; unsigned hmask = 0;
-    A tx = A(0); bool uns = false, bad = false;
-#pragma unroll
-    for (int k = 0; k < SG_ITEMS; ++k) {
-      const long long g = (long long)gl[k];
-      const bool head = (k == 0 && base == 0) || g != prev;
-      uns |= g < prev && !(k == 0 && base == 0);
-      bad |= (unsigned long long)g >= (unsigned long long)p.size;
-      prev = g;
-      A v;
-      if (VK == 2) { double d = __longlong_as_double((long long)raw[k]); if (NANSKIP && d != d) d = OP == SC_SUM ? 0.0 : 1.0; v = (A)d; }
-      else v = (A)(long long)(raw[k] ^ keyflip);
-      tx = (k == 0 || head) ? v : ScanOp<A, OP>::apply(tx, v);
-      hmask |= head ? (1u << k) : 0u;
-      x[k] = tx;
-    }
-    if (uns) *p.unsorted_w = 1;                                          // (the kernel finishes its pass anyway: every tile publishes)
-    if (bad) p.status[AGC_ST_BADLABEL] = 1;
-    bool pf, have_p, agg_f; A px, agg_x;
-    block_seg_scan<A, OP>(hmask != 0u, tx, pf, px, have_p, agg_f, agg_x);   // every thread is past its reads of stage s after this
-    if (t == 0) {
-      desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
-      const int next = (it + SP_STAGES) * grid + cta;
-      if (next < nfull) issue(s, next);
-    }
-    if (owe) settle(lm, lxb);
-#pragma unroll
-    for (int k = 0; k < SG_ITEMS; ++k) xp[k] = x[k];
-    hmask_p = hmask; pf_p = pf; have_p_p = have_p; px_p = px; aggf_p = agg_f; aggx_p = agg_x; tp = tile; owe = true;
-  }
-  if (owe) {
-    unsigned long long lm = 2ull, lxb = 0ull;
-    if (t < 32 && tp - 1 - lane >= 0) desc_load(desc + 2 * (long long)(tp - 1 - lane), lm, lxb);
-    settle(lm, lxb);
-  }
-  if (t == 0) sp_store_done();
-}
-
 // ---------------------------------------------------------------------------------------------
-// k_seg_scan_ws: k_seg_scan_pipe without a single CTA-wide barrier -- the same TMA ring, tiles and descriptors, but the
-// block-level part of the scan, the look-back and the loads belong to a NINTH warp.  ncu on k_seg_scan_pipe (r2q): the
-// memory pipeline never runs dry (its mbarrier wait succeeds at the first try, always); what bounds the kernel is the
-// serial path of a CTA through one tile -- four barriers, the warp-0 look-back with seven warps waiting (28 % of all
-// stall samples), the serial folds of the block scan -- 2.4 us per 2048 elements, two CTAs per SM.  Here
+// k_seg_scan_ws: the persistent chained scan without a single CTA-wide barrier -- the block-level part of the scan, the
+// look-back and the loads belong to a NINTH warp.  ncu on its predecessor with the CTA-wide structure (r2q): the memory
+// pipeline never runs dry (the mbarrier wait succeeds at the first try, always); what bounds that kernel is the serial path
+// of a CTA through one tile -- four barriers, the warp-0 look-back with seven warps waiting (28 % of all stall samples), the
+// serial folds of the block scan -- 2.4 us per 2048 elements, two CTAs per SM.  Here
 //   * the 8 data warps read their 256 elements, scan them with shuffles, hand (flag, value) of the warp to the ninth
 //     warp through shared memory + an mbarrier arrive, and go straight on to the NEXT tile; one tile later they pick up
 //     their warp's exclusive prefix (carry included), finish the owed results and store their own 2 KB slice with a
@@ -1081,7 +958,8 @@ __global__ void __launch_bounds__(SG_THREADS, 2) k_seg_scan_pipe(const ScanParam
 //   * the ninth warp waits for the 8 arrivals, scans the 8 warp aggregates, refills the stage the tile occupied (its
 //     readers have all arrived), publishes the tile's descriptor, runs the look-back (requested before the wait), publishes
 //     the prefix and posts the 8 warp prefixes.
-// Slots are double-buffered by tile parity; a data warp is at most one tile ahead of the ninth warp.
+// Slots are double-buffered by tile parity; a data warp is at most one tile ahead of the ninth warp.  Launched cooperatively
+// (all CTAs resident, see the prologue).
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_THREADS = SG_THREADS + 32;
 constexpr int WS_SMEM = 115712;                                   // two CTAs per SM: (228 KB - 2 * 1 KB reserved) / 2; 496 B of small state + alignment + 7 tile buffers
@@ -1121,6 +999,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams 
     sp_mbar_init(bar_pre, 1); sp_mbar_init(bar_pre + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sp_fence_async();
+    // Tiles go round robin: iteration `it` of CTA b owns tile it * gridDim + b, so that neighbouring tiles are worked on at the
+    // same time by neighbouring CTAs.  The launch is COOPERATIVE: the runtime guarantees that every CTA of the grid is resident,
+    // so every tile a look-back waits for is being worked on.  (Measured alternatives: tickets from a counter, three taken
+    // back to back at the start -- CTA 0 held tiles 0, 1, 2 and CTA 1 waited two iterations for tile 2; tickets taken one
+    // dependent atomic after the other -- 1.84 ms against 1.31: with tickets drawn three tiles ahead the order in which
+    // tiles are WORKED ON drifts away from the order in which they were drawn, and everybody waits for the oldest one.)
 #pragma unroll
     for (int s = 0; s < SP_STAGES; ++s) { const int tile = s * grid + cta; if (tile < nfull) issue(s, tile); }
   }
@@ -1486,30 +1370,30 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
           unsigned long long* d = (unsigned long long*)(ws + L.desc);
           const bool ns = (p.flags & AGC_F_NANSKIP) != 0;
           AGC_COUNT_LAUNCH(1);
-          // AGC_SCAN_PIPE=0: the one-tile-per-CTA kernel (k_seg_scan_lean); AGC_SCAN_WS=0: the persistent kernel with CTA barriers
+          // AGC_SCAN_WS=0: the one-tile-per-CTA kernel (k_seg_scan_lean) instead of the persistent warp-specialised one
           static const int occ = getenv("AGC_SCAN_OCC") ? atoi(getenv("AGC_SCAN_OCC")) : 6;
-          static const bool pipe_env = !(getenv("AGC_SCAN_PIPE") && atoi(getenv("AGC_SCAN_PIPE")) == 0);
           static const bool ws_on = !(getenv("AGC_SCAN_WS") && atoi(getenv("AGC_SCAN_WS")) == 0);
-          CUtensorMap tml, tmv, tmo, tmo32;                      // tiles of 256 rows x 64 bytes (64-byte swizzle); tmo32: one warp's 32 rows of the result
-          const bool pipe_on = pipe_env && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo, p.out, nfull);
-          const bool ws_ok = pipe_on && ws_on && sp_tile_map(&tmo32, p.out, nfull, 32);
-          // the persistent kernels walk the tiles round robin and wait for their neighbours: every CTA of the grid must be
-          // resident, so the grid is what the occupancy calculator grants (two CTAs per SM), never more
+          CUtensorMap tml, tmv, tmo32;                           // tiles of 256 rows x 64 bytes (64-byte swizzle); tmo32: one warp's 32 rows of the result
+          const bool ws_ok = ws_on && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo32, p.out, nfull, 32);
+          // cooperative launch: the runtime refuses a grid that cannot be resident as a whole (then the one-tile-per-CTA kernel
+          // runs) and never starts part of it -- the round-robin tile order of the kernel depends on exactly that
 #define AGC_PIPE(VK_, NS_)                                                                                              \
           { static std::atomic<unsigned long long> attr_done{0};                                                           \
             int per_sm = 0;                                                                                                \
-            if (ws_ok) { ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_>, WS_SMEM, attr_done);                              \
-              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_ws<A, OP, VK_, NS_>, WS_THREADS, WS_SMEM); } \
-            else { ensure_dyn_smem(k_seg_scan_pipe<A, OP, VK_, NS_>, SP_SMEM, attr_done);                                  \
-              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_pipe<A, OP, VK_, NS_>, SG_THREADS, SP_SMEM); } \
+            if (ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_>, WS_SMEM, attr_done))                                       \
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_ws<A, OP, VK_, NS_>, WS_THREADS, WS_SMEM);  \
             const long long cap = (long long)per_sm * device_sms();                                                        \
             const int pgrid = (int)(nfull < cap ? nfull : cap);                                                            \
-            if (pgrid <= 0) launched = false;                                                                              \
-            else if (ws_ok) k_seg_scan_ws<A, OP, VK_, NS_><<<pgrid, WS_THREADS, WS_SMEM, st>>>(p, d, nfull, tml, tmv, tmo32); \
-            else k_seg_scan_pipe<A, OP, VK_, NS_><<<pgrid, SG_THREADS, SP_SMEM, st>>>(p, d, nfull, tml, tmv, tmo); }
+            launched = false;                                                                                              \
+            if (pgrid > 0) {                                                                                               \
+              ScanParams pa = p; unsigned long long* da = d; int nf = nfull;                                               \
+              void* args[] = {&pa, &da, &nf, &tml, &tmv, &tmo32};                                                          \
+              launched = cudaLaunchCooperativeKernel((const void*)k_seg_scan_ws<A, OP, VK_, NS_>, dim3(pgrid), dim3(WS_THREADS), args, WS_SMEM, st) == cudaSuccess; \
+              if (!launched) cudaGetLastError();                                                                           \
+            } }
 #define AGC_LEAN(VK_, NS_)                                                                                              \
-          { bool launched = pipe_on;                                                                                       \
-            if (pipe_on) AGC_PIPE(VK_, NS_)                                                                                \
+          { bool launched = ws_ok;                                                                                         \
+            if (ws_ok) AGC_PIPE(VK_, NS_)                                                                                  \
             if (launched) {}                                                                                               \
             else if (occ == 5) k_seg_scan_lean<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
             else k_seg_scan_lean<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d); }
