@@ -152,15 +152,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long l
   }
 }
 
-template <class K>
-__global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, const unsigned* vin, K* kout, unsigned* vout, long long n, int shift,
+template <class K, class V = unsigned>
+__global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, const V* vin, K* kout, V* vout, long long n, int shift,
                                                              const unsigned* offs, int nblocks, const int* run_flag) {
   if (run_flag && *run_flag == 0) return;
   constexpr int ITEMS = RsCfg<K>::ITEMS, TILE = RsCfg<K>::TILE;
   extern __shared__ __align__(16) unsigned char rs_smem[];
-  K* skey = (K*)rs_smem;                                          // [TILE] tile in digit order
-  unsigned* sval = (unsigned*)(skey + TILE);                      // [TILE]
-  unsigned* cnt = sval + TILE;                                    // [RS_WARPS][256] per-warp digit counters -> tile-local bases
+  V* sval = (V*)rs_smem;                                          // [TILE] tile in digit order (the wider type first: alignment)
+  K* skey = (K*)(sval + TILE);                                    // [TILE]
+  unsigned* cnt = (unsigned*)(skey + TILE);                       // [RS_WARPS][256] per-warp digit counters -> tile-local bases
   unsigned* dstart = cnt + RS_WARPS * 256;                        // [256] tile-local start of every digit
   unsigned* gbase = dstart + 256;                                 // [256] global position of the digit's first element of this tile
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, c
     __syncthreads();
     const long long tile0 = (long long)tile * TILE;
     const long long wbase = tile0 + (long long)w * (ITEMS * 32);
-    K key[ITEMS]; unsigned val[ITEMS]; unsigned short rnk[ITEMS];
+    K key[ITEMS]; V val[ITEMS]; unsigned short rnk[ITEMS];
     unsigned* mycnt = cnt + w * 256;
     const unsigned lt = (1u << lane) - 1u;
   #pragma unroll
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, c
       const long long i = wbase + j * 32 + lane;
       const bool valid = i < n;
       key[j] = valid ? kin[i] : K(0);
-      val[j] = valid ? vin[i] : 0u;
+      val[j] = valid ? vin[i] : V(0);
     }
   #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, c
     __syncthreads();
   }
 }
-template <class K> inline size_t rs_scatter_smem() { return (size_t)RsCfg<K>::TILE * (sizeof(K) + 4) + (RS_WARPS * 256 + 512) * 4; }
+template <class K, class V = unsigned> inline size_t rs_scatter_smem() { return (size_t)RsCfg<K>::TILE * (sizeof(K) + sizeof(V)) + (RS_WARPS * 256 + 512) * 4; }
 
 struct SortBufs {
   void* k[2]; unsigned* v[2]; unsigned* hist; unsigned* tile_sums;
@@ -271,7 +271,16 @@ __global__ void k_group_keys(Indexer ix, long long n, unsigned* keys, unsigned* 
   if (bad) status[AGC_ST_BADLABEL] = 1;
   if (uns) *unsorted = 1;
 }
-__global__ void k_zero_int(int* p) { *p = 0; }
+__global__ void k_zero_int(int* p) { p[0] = 0; p[1] = 0; }
+// 4096 neighbouring pairs spread over the labels: random labels show an inversion here with certainty, and the persistent
+// direct scan (which finishes its pass once started) then never starts
+template <class LT>
+__global__ void k_sorted_sample(const LT* labels, long long n, int* unsorted) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x, m = (long long)gridDim.x * blockDim.x;
+  if (n < 2) return;
+  const long long i = (long long)((double)t / (double)m * (double)(n - 1));
+  if (labels[i + 1] < labels[i]) { unsorted[0] = 1; unsorted[1] = 1; }
+}
 __global__ void k_report_unsorted(const int* unsorted, int* status) { if (*unsorted) status[AGC_ST_UNSORTED] = 1; }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,6 +312,8 @@ struct ScanParams {
   int lb_sleep;                                       // chained scan: nanoseconds a look-back lane sleeps before it polls an unpublished descriptor again
   int tile0;                                          // direct scan: tile of block 0 (the persistent chained kernel took the tiles before it)
   void* gath;                                         // keys path: scan inputs in sorted order (PHASE 0 gathers them once)
+  void* stage;                                        // keys path, labels really unsorted: results in SORTED order (out dtype); the
+                                                      // windowed un-sort below brings them home instead of one random store each
 };
 
 // element k of the sorted sequence -> the value fed to the scan (A = double for float sum/prod,
@@ -442,8 +453,43 @@ __global__ void __launch_bounds__(SG_THREADS) k_seg_scan(const ScanParams p, uns
     if (i >= p.n) break;
     if (h[k]) open = false;
     A r = open ? ScanOp<A, OP>::apply(pre, x[k]) : x[k];
-    scan_store<A, OP>(p, (long long)ps[k], r);
+    if (p.stage && sel) { ScanParams q = p; q.out = p.stage; scan_store<A, OP>(q, i, r); }
+    else scan_store<A, OP>(p, (long long)ps[k], r);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Un-sort: out[pos[k]] = staged[k].  Done naively this is one random 8-byte store per element over the whole output (2 GB
+// at N = 2^28): 18 of the 30 ms of an unsorted cumsum, 85 % of the store sectors missing L2 and paying a read-modify-write.
+// Instead (pos, value) is partitioned by the top 8 bits of pos with one pass of the radix scatter (coalesced), and the
+// partitioned records are then stored by CTAs that walk them IN ORDER: the CTAs resident at any time work on a few
+// neighbouring output windows (8 MB each at N = 2^28), which stay in L2 until their sectors are complete.
+// ---------------------------------------------------------------------------------------------
+template <class V>
+__global__ void __launch_bounds__(256) k_window_scatter(const unsigned* pos, const V* val, long long n, V* out, const int* run_flag) {
+  if (run_flag && *run_flag == 0) return;
+  // one CTA per 8192 records, started in blockIdx order: the CTAs resident together cover a few neighbouring windows.
+  // (A persistent grid walking the chunks round robin measured 10.1 ms against 4.3: its CTAs drift apart and touch many
+  //  windows at once -- DRAM traffic 19 GB against 11.6.)
+  const long long base = (long long)blockIdx.x * 8192;
+#pragma unroll 4
+  for (int c = 0; c < 32; ++c) {
+    const long long i = base + c * 256 + threadIdx.x;
+    if (i < n) out[pos[i]] = val[i];
+  }
+}
+template <class V>
+inline void unsort_windowed(const unsigned* pos, const V* staged, long long n, V* out, unsigned* pos_part, V* val_part,
+                            unsigned* hist, unsigned* tile_sums, const int* run_flag, cudaStream_t st) {
+  int bits = 1; while (bits < 32 && (1ll << bits) < n) ++bits;
+  const int shift = bits > 8 ? bits - 8 : 0;
+  const int nb = rs_blocks_k<unsigned>(n);
+  static std::atomic<unsigned long long> attr_done{0};
+  ensure_dyn_smem(k_radix_scatter<unsigned, V>, (int)rs_scatter_smem<unsigned, V>(), attr_done);
+  AGC_COUNT_LAUNCH(1), k_radix_hist<unsigned><<<tile_grid(nb, 4), RS_THREADS, 0, st>>>(pos, n, shift, hist, nb, run_flag);
+  exclusive_scan_u32(hist, 256ll * nb, tile_sums, st, run_flag);
+  AGC_COUNT_LAUNCH(1), k_radix_scatter<unsigned, V><<<tile_grid(nb, 2), RS_THREADS, rs_scatter_smem<unsigned, V>(), st>>>(pos, staged, pos_part, val_part, n, shift, hist, nb, run_flag);
+  AGC_COUNT_LAUNCH(1), k_window_scatter<V><<<(unsigned)((n + 8191) / 8192), 256, 0, st>>>(pos_part, val_part, n, out, run_flag);
 }
 
 // ---- vectorised element access for the direct scan: 8 consecutive elements per thread as 128-bit loads ----
@@ -984,6 +1030,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams 
   const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
   const unsigned long long keyflip = (VK == 1 && (OP == SC_MAX || OP == SC_MIN)) ? 0x8000000000000000ull : 0ull;
   const unsigned bar_full = sp_saddr(s_bar), bar_agg = sp_saddr(s_bar + 3), bar_pre = sp_saddr(s_bar + 5);
+  // the sampled pre-check already found an inversion: this word is written by that kernel only, so every thread of every CTA
+  // reads the same value (the run-time flag p.unsorted may come up while the kernel runs -- leaving on it would strand the
+  // CTAs that wait for this one's tiles)
+  if (p.unsorted[1]) return;
   const unsigned sleep_ns = (unsigned)p.lb_sleep & 0xffffu; const bool gpu_scope = (p.lb_sleep >> 30) & 1;
   auto issue = [&](int s, int tile) {
     const unsigned bar = bar_full + 8 * s;
@@ -1265,7 +1315,7 @@ __global__ void k_pos_select(const unsigned* p0, const unsigned* p1, const int* 
 // ---------------------------------------------------------------------------------------------
 inline int64_t al256(int64_t x) { return (x + 255) / 256 * 256; }
 struct ScanWs {
-  int64_t k32[2], v[2], k64[2], v2[2], slot, gath, hist, tsum, tile_f, tile_x, carry_f, carry_x, desc, flag, total;
+  int64_t k32[2], v[2], k64[2], v2[2], slot, gath, hist, tsum, tile_f, tile_x, carry_f, carry_x, desc, flag, stage, total;
 };
 inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   ScanWs w; int64_t o = 0;
@@ -1275,6 +1325,7 @@ inline ScanWs scan_ws_layout(long long n, bool want_sort_op) {
   if (want_sort_op) { w.k64[0] = take(n * 8); w.k64[1] = take(n * 8); w.v2[0] = take(n * 4); w.v2[1] = take(n * 4); w.slot = take(n * 4); }
   else { w.k64[0] = w.k64[1] = w.v2[0] = w.v2[1] = w.slot = 0; }
   w.gath = want_sort_op ? 0 : take(n * 8);
+  w.stage = want_sort_op ? 0 : take(n * 8);
   w.hist = take(256ll * nb * 4); w.tsum = take((xs_tiles(256ll * nb) + 1) * 4);
   const long long ntiles = (n + SG_TILE - 1) / SG_TILE + 1;
   w.tile_f = take(ntiles); w.tile_x = take(ntiles * 8); w.carry_f = take(ntiles); w.carry_x = take(ntiles * 8);
@@ -1319,6 +1370,14 @@ inline void run_seg_scan(const ScanParams& p, char* ws, const ScanWs& L, cudaStr
   AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 0><<<ntiles, SG_THREADS, 0, st>>>(p, tf, tx, nullptr, nullptr);
   AGC_COUNT_LAUNCH(1), k_seg_scan_tiles<A, OP><<<1, 1024, 0, st>>>(tf, tx, ntiles, cf, cx, p.only_if_unsorted ? p.unsorted : nullptr, 1);
   AGC_COUNT_LAUNCH(1), k_seg_scan<A, OP, 1><<<ntiles, SG_THREADS, 0, st>>>(p, nullptr, nullptr, cf, cx);
+  if (p.stage) {                                             // (every kernel below is a no-op unless the labels really were unsorted)
+    const int eb = dtype_bytes(p.out_dtype);
+    unsigned* hist = (unsigned*)(ws + L.hist); unsigned* tsum = (unsigned*)(ws + L.tsum);
+    // free by now: the pair of sort buffers that does not hold the result, and the gathered inputs
+    unsigned* pos_part = (unsigned*)(ws + (p.pos[1] == (const unsigned*)(ws + L.v[1]) ? L.k32[0] : L.k32[1]));
+    if (eb == 8) unsort_windowed<unsigned long long>(p.pos[1], (const unsigned long long*)p.stage, p.n, (unsigned long long*)p.out, pos_part, (unsigned long long*)p.gath, hist, tsum, p.unsorted, st);
+    else unsort_windowed<unsigned>(p.pos[1], (const unsigned*)p.stage, p.n, (unsigned*)p.out, pos_part, (unsigned*)p.gath, hist, tsum, p.unsorted, st);
+  }
 }
 
 // AGC_SCAN_CHAIN=0 (or agc_tuning key 6 = 0) selects the three-kernel direct scan instead of the chained single pass
@@ -1458,6 +1517,10 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
   if (direct_lt) {
     flag = (int*)(ws + L.flag);
     AGC_COUNT_LAUNCH(1), k_zero_int<<<1, 1, 0, st>>>(flag);
+    if (n >= (1ll << 20)) {
+      if (direct_lt == 8) AGC_COUNT_LAUNCH(1), k_sorted_sample<long long><<<16, 256, 0, st>>>((const long long*)r->index.labels, n, flag);
+      else AGC_COUNT_LAUNCH(1), k_sorted_sample<int><<<16, 256, 0, st>>>((const int*)r->index.labels, n, flag);
+    }
     p.unsorted = flag; p.unsorted_w = flag;
     dispatch_seg_scan(r, p, ws, L, st, direct_lt);
     if (r->flags & AGC_F_ASSUME_SORTED) { AGC_COUNT_LAUNCH(1), k_report_unsorted<<<1, 1, 0, st>>>(flag, r->status); return 0; }
@@ -1489,6 +1552,9 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
   p.keys[0] = keys[0]; p.keys[1] = keys[1]; p.pos[0] = pos[0]; p.pos[1] = pos[1]; p.unsorted = flag;
   p.only_if_unsorted = direct_lt != 0;
   p.gath = ws + L.gath;
+  { static const bool win = !(getenv("AGC_UNSORT_WINDOW") && atoi(getenv("AGC_UNSORT_WINDOW")) == 0);
+    const int eb = dtype_bytes(r->out_dtype);
+    p.stage = (win && n >= (1ll << 22) && (eb == 8 || eb == 4)) ? (void*)(ws + L.stage) : nullptr; }
   if (r->op < AGC_OP_CUMSUM || r->op > AGC_OP_CUMMIN) { g_scan_err = "unknown N->N op"; return -2; }
   dispatch_seg_scan(r, p, ws, L, st, 0);
   return 0;
