@@ -207,10 +207,13 @@ int         agc_owner_pack(const agc_request_t* req, int64_t* carrier, int32_t u
 int         agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_t* dst);
 
 /* measurement hooks (bench.py): when enabled, agc_aggregate brackets its dominant accumulate kernel with
- * CUDA events on the caller's stream; agc_profile_last_ms() waits for that kernel and returns its duration.
+ * CUDA events on the caller's stream -- a ring of 64 pairs, one per call, so a timed loop needs no read-back;
+ * agc_profile_ms(back) waits for the call `back` calls ago (0 = the last one) and returns its duration,
+ * agc_profile_last_ms() = agc_profile_ms(0).
  * agc_launch_count() = number of libaggcuda kernels launched by this process so far. */
 int         agc_profile_enable(int on);
 float       agc_profile_last_ms(void);
+float       agc_profile_ms(int back);
 int64_t     agc_launch_count(void);
 /* kernel-selection knobs for A/B measurements and tests; value < 0 only reads.  Returns the (new) value.
  *   key 0  strategy for tables larger than one SM's shared memory: 0 hot-key cache, 1 on-device label probe

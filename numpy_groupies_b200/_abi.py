@@ -53,7 +53,7 @@ PK_COPY, PK_NEG, PK_FLAG, PK_NEGFLAG = 0, 1, 2, 3
 
 EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_partials", "agc_aggregate",
            "agc_label_minmax", "agc_unpack", "agc_group_order_workspace_bytes", "agc_group_order",
-           "agc_profile_enable", "agc_profile_last_ms", "agc_launch_count", "agc_tuning",
+           "agc_profile_enable", "agc_profile_last_ms", "agc_profile_ms", "agc_launch_count", "agc_tuning",
            "agc_label_scan_workspace_bytes", "agc_label_scan", "agc_mark_present", "agc_multi_arange",
            "agc_pack_tables", "agc_rank_fold", "agc_apply_carry", "agc_owner_pack", "agc_ordered_accumulate",
            "agc_host_narrow_labels")
@@ -117,6 +117,8 @@ def load():
     lib.agc_profile_enable.restype = C.c_int
     lib.agc_profile_enable.argtypes = [C.c_int]
     lib.agc_profile_last_ms.restype = C.c_float
+    lib.agc_profile_ms.restype = C.c_float
+    lib.agc_profile_ms.argtypes = [C.c_int]
     lib.agc_launch_count.restype = C.c_int64
     lib.agc_tuning.restype = C.c_int
     lib.agc_tuning.argtypes = [C.c_int, C.c_int]

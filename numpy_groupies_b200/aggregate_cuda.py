@@ -14,8 +14,11 @@ CUDA tensor; nothing crosses PCIe except the 32-byte status record).
 
 Extra keyword arguments beyond the reference's (it already takes ``**kwargs``):
   check=True          read the device status record after the call (one stream sync) and raise
-                      ValueError for bad labels, as the reference does.  ``check=False`` keeps the
-                      call asynchronous; bad labels are then ignored silently.
+                      ValueError for bad labels, as the reference does.  Whether labels are valid depends on the labels and
+                      ``size`` alone, so a CUDA label tensor that passed is remembered (same tensor object, same torch
+                      version counter -- any in-place write bumps it): later calls on it stay asynchronous.
+                      ``check="always"`` reads the record back on every call; ``check=False`` never does (bad labels
+                      are then ignored silently).
   assume_sorted=False promise non-decreasing flat labels (N->N functions skip the sort; verified).
   fast=True           allow the shared-memory fast kernels (False forces the general path).
   deterministic=False fixed-order mode: floating sum / mean / var / std / sumofsquares / prod add every group's elements in
@@ -114,6 +117,53 @@ class _Dev:
 
 def _is_tensor(x):
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+# ---- labels that already passed the bad-label / sortedness check --------------------------------------------------
+# The verdict of the check is a function of (labels, size, form) only.  Remembering it per label TENSOR -- weak reference to
+# the very object plus its version counter, which every in-place torch operation on it or on a view of it bumps -- lets
+# repeated calls on the same labels (group-by over many value columns, the steps of a training loop) run without the one
+# host synchronisation a call otherwise has.  A new tensor object, even at the same address, is always checked again.
+_VALID = {}
+
+
+def _valid_sig(c):
+    plan = c.plan
+    return (plan.form, plan.flat_size, tuple(getattr(plan, "dims", None) or ()), getattr(plan, "axis", None), bool(c.assume_sorted))
+
+
+def _want_check(c):
+    """Does this call have to read the status record back?"""
+    if c.check is False:
+        return False
+    g = c.group_idx
+    if c.check == "always" or not (_is_tensor(g) and getattr(g, "is_cuda", False)):
+        return True
+    e = _VALID.get(id(g))
+    if e is None:
+        return True
+    ref, ver, sigs = e
+    if ref() is not g or ver != g._version:
+        _VALID.pop(id(g), None)
+        return True
+    return _valid_sig(c) not in sigs
+
+
+def _mark_validated(c):
+    g = c.group_idx
+    if not (_is_tensor(g) and getattr(g, "is_cuda", False)) or c.check is False:
+        return
+    import weakref
+    e = _VALID.get(id(g))
+    if e is not None and e[0]() is g and e[1] == g._version:
+        e[2].add(_valid_sig(c))
+        return
+    if len(_VALID) > 256:
+        _VALID.clear()
+    try:
+        _VALID[id(g)] = (weakref.ref(g), g._version, {_valid_sig(c)})
+    except TypeError:                                       # (an object that cannot be weakly referenced: never cached)
+        pass
 
 
 _TORCH_NP = {}
@@ -609,12 +659,13 @@ def _run_device(c):
             if rc == -20:
                 raise NotImplementedError(msg)
             raise RuntimeError(f"agc_aggregate failed ({rc}): {msg}")
-        if c.check:
+        if _want_check(c):
             st = status.cpu().numpy()
             if st[_abi.ST_BADLABEL]:
                 raise ValueError("group_idx contains negative indices or indices too large for size")
             if st[_abi.ST_UNSORTED]:
                 raise ValueError("assume_sorted=True but group_idx is not sorted")
+            _mark_validated(c)
             c.regime = int(st[_abi.ST_REGIME])
             _LAST["regime"] = c.regime
             _LAST["probe"] = tuple(int(v) for v in st[4:7])
@@ -934,10 +985,11 @@ def _fused_family(group_idx, a, members, family, size, fill_value, order, axis, 
             for nm in members:
                 if bases[nm] in ("var", "std"):
                     results[nm] = finish(nm)
-        if c0.check:
+        if _want_check(c0):
             st = status.cpu().numpy()
             if st[_abi.ST_BADLABEL]:
                 raise ValueError("group_idx contains negative indices or indices too large for size")
+            _mark_validated(c0)
             _LAST["regime"] = int(st[_abi.ST_REGIME])
     final = {}
     for nm, o in results.items():

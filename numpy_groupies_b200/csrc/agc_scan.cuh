@@ -134,8 +134,10 @@ inline int rs_blocks(long long n) { return (int)((n + RS_TILE_MIN - 1) / RS_TILE
 template <class K> inline int rs_blocks_k(long long n) { return (int)((n + RsCfg<K>::TILE - 1) / RsCfg<K>::TILE); }
 
 template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long long n, int shift, unsigned* hist, int nblocks, const int* run_flag) {
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long long n, int shift, unsigned* hist, int nblocks, const int* run_flag,
+                                                           const K* bias_p = nullptr) {
   if (run_flag && *run_flag == 0) return;
+  const K bias = bias_p ? *bias_p : K(0);                      // keys are sorted as (key - bias): see value_sort_range
   __shared__ unsigned h[256];
   for (int tile = blockIdx.x; tile < nblocks; tile += gridDim.x) {
     if (threadIdx.x < 256) h[threadIdx.x] = 0;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long l
 #pragma unroll 4
     for (int c = 0; c < RsCfg<K>::ITEMS; ++c) {
       const long long i = base + c * RS_THREADS + threadIdx.x;
-      if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 0xffu], 1u);
+      if (i < n) atomicAdd(&h[(unsigned)((K)(keys[i] - bias) >> shift) & 0xffu], 1u);
     }
     __syncthreads();
     if (threadIdx.x < 256) hist[(long long)threadIdx.x * nblocks + tile] = h[threadIdx.x];
@@ -154,8 +156,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K* keys, long l
 
 template <class K, class V = unsigned>
 __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, const V* vin, K* kout, V* vout, long long n, int shift,
-                                                             const unsigned* offs, int nblocks, const int* run_flag) {
+                                                             const unsigned* offs, int nblocks, const int* run_flag, const K* bias_p = nullptr) {
   if (run_flag && *run_flag == 0) return;
+  const K bias = bias_p ? *bias_p : K(0);
   constexpr int ITEMS = RsCfg<K>::ITEMS, TILE = RsCfg<K>::TILE;
   extern __shared__ __align__(16) unsigned char rs_smem[];
   V* sval = (V*)rs_smem;                                          // [TILE] tile in digit order (the wider type first: alignment)
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, c
   #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const bool valid = wbase + j * 32 + lane < n;
-      const unsigned d = valid ? ((unsigned)(key[j] >> shift) & 0xffu) : (256u + lane);
+      const unsigned d = valid ? ((unsigned)((K)(key[j] - bias) >> shift) & 0xffu) : (256u + lane);
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       const int leader = __ffs(peers) - 1;
       unsigned old = 0;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, c
   #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       if (wbase + j * 32 + lane < n) {
-        const unsigned d = (unsigned)(key[j] >> shift) & 0xffu;
+        const unsigned d = (unsigned)((K)(key[j] - bias) >> shift) & 0xffu;
         const unsigned lp = dstart[d] + mycnt[d] + rnk[j];
         skey[lp] = key[j]; sval[lp] = val[j];
       }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(const K* kin, c
     const int count = (int)(n - tile0 < TILE ? n - tile0 : TILE);
     for (int lp = threadIdx.x; lp < count; lp += RS_THREADS) {
       const K k = skey[lp];
-      const unsigned d = (unsigned)(k >> shift) & 0xffu;
+      const unsigned d = (unsigned)((K)(k - bias) >> shift) & 0xffu;
       const long long pos = (long long)gbase[d] + (lp - dstart[d]);
       kout[pos] = k; vout[pos] = sval[lp];
     }
@@ -239,17 +242,22 @@ struct SortBufs {
 };
 // sorts bits [lo_bit, hi_bit) ; returns which buffer (0/1) holds the result. run_flag (device int, may be
 // NULL) == 0 turns every kernel into a no-op, in which case the data stays in buffer `src`.
+// pass_flags (device int per pass, may be NULL) replaces run_flag pass by pass; bias (device K, may be NULL) is subtracted
+// from every key before its digit is taken.
 template <class K>
-inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int hi_bit, const int* run_flag, cudaStream_t st) {
+inline int radix_sort_pairs(SortBufs& b, int src, long long n, int lo_bit, int hi_bit, const int* run_flag, cudaStream_t st,
+                            const int* pass_flags = nullptr, const K* bias = nullptr) {
   if (n == 0) return src;
   const int nb = rs_blocks_k<K>(n);
   static std::atomic<unsigned long long> attr_done{0};
   ensure_dyn_smem(k_radix_scatter<K>, (int)rs_scatter_smem<K>(), attr_done);
-  for (int shift = lo_bit; shift < hi_bit; shift += 8) {
-    AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<tile_grid(nb, 4), RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, run_flag);
-    exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st, run_flag);
+  int pass = 0;
+  for (int shift = lo_bit; shift < hi_bit; shift += 8, ++pass) {
+    const int* rf = pass_flags ? pass_flags + pass : run_flag;
+    AGC_COUNT_LAUNCH(1), k_radix_hist<K><<<tile_grid(nb, 4), RS_THREADS, 0, st>>>((const K*)b.k[src], n, shift, b.hist, nb, rf, bias);
+    exclusive_scan_u32(b.hist, 256ll * nb, b.tile_sums, st, rf);
     AGC_COUNT_LAUNCH(1), k_radix_scatter<K><<<tile_grid(nb, 2), RS_THREADS, rs_scatter_smem<K>(), st>>>((const K*)b.k[src], b.v[src], (K*)b.k[src ^ 1], b.v[src ^ 1], n, shift,
-                                                   b.hist, nb, run_flag);
+                                                   b.hist, nb, rf, bias);
     src ^= 1;
   }
   return src;
@@ -1256,19 +1264,64 @@ __global__ void __launch_bounds__(1024) k_seg_scan_tiles(const unsigned char* ti
 // ---------------------------------------------------------------------------------------------
 // func='sort' helpers
 // ---------------------------------------------------------------------------------------------
-__global__ void k_value_keys(const void* a, int a_dtype, long long n, int reverse, unsigned long long* keys, unsigned* pos) {
+// range[0] / range[1] (may be NULL): smallest / largest key, for the range-compressed sort of integer values
+__global__ void k_value_keys(const void* a, int a_dtype, long long n, int reverse, unsigned long long* keys, unsigned* pos,
+                             unsigned long long* range) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long lo = 0xffffffffffffffffull, hi = 0ull;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
     unsigned long long u;
     bool nan = false;
-    if (a_dtype == AGC_DT_F32) { float v = ((const float*)a)[i]; nan = v != v; u = (unsigned long long)key_of((double)v) ^ 0x8000000000000000ull; }
-    else if (a_dtype == AGC_DT_F64) { double v = ((const double*)a)[i]; nan = v != v; u = (unsigned long long)key_of(v) ^ 0x8000000000000000ull; }
-    else if (a_dtype == AGC_DT_U64) u = ((const unsigned long long*)a)[i];
-    else u = (unsigned long long)load_int(a, a_dtype, i) ^ 0x8000000000000000ull;
-    if (reverse) u = ~u;
+    // reverse: the reference sorts -a (aggregate_numpy.py:210-214, np.lexsort((-a, group_idx))), and for integers numpy's
+    // negation WRAPS in the array's own width: the most negative value of a signed type and 0 of an unsigned type are their
+    // own negatives and stay in front.  Floats: -a is exact, the key's order simply flips; NaNs sort last either way.
+    if (a_dtype == AGC_DT_F32) { float v = ((const float*)a)[i]; nan = v != v; u = (unsigned long long)key_of((double)v) ^ 0x8000000000000000ull; if (reverse) u = ~u; }
+    else if (a_dtype == AGC_DT_F64) { double v = ((const double*)a)[i]; nan = v != v; u = (unsigned long long)key_of(v) ^ 0x8000000000000000ull; if (reverse) u = ~u; }
+    else if (a_dtype == AGC_DT_U64) { u = ((const unsigned long long*)a)[i]; if (reverse) u = 0ull - u; }
+    else {
+      long long v = load_int(a, a_dtype, i);
+      if (reverse) {
+        const int bits = 8 * dtype_bytes(a_dtype);
+        const bool uns = a_dtype == AGC_DT_U8 || a_dtype == AGC_DT_U16 || a_dtype == AGC_DT_U32 || a_dtype == AGC_DT_BOOL;
+        unsigned long long w = 0ull - (unsigned long long)v;
+        if (bits < 64) {
+          w &= (1ull << bits) - 1ull;
+          if (!uns && (w >> (bits - 1))) w |= ~((1ull << bits) - 1ull);     // sign-extend from the array's width
+        }
+        v = (long long)w;
+      }
+      u = (unsigned long long)v ^ 0x8000000000000000ull;
+    }
     if (nan) u = 0xffffffffffffffffull;                  // NaNs sort last in both directions (np.lexsort)
     keys[i] = u; pos[i] = (unsigned)i;
+    lo = u < lo ? u : lo; hi = u > hi ? u : hi;
   }
+  if (range) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(range, lo); atomicMax(range + 1, hi); }
+  }
+}
+// Range-compressed value sort: integer values rarely use all 64 bits of their key (the C4 workload: int64 holding 32-bit
+// numbers), and every 8 bits the span max - min does not reach are a radix pass (6.5 ms at N = 2^28) that moves nothing.  The
+// passes sort (key - min); pass p runs iff 8p < bits(max - min).  The skipped passes are a SUFFIX, so which buffer holds the
+// result follows from the number of passes run: flags[8] says whether that number is odd (then k_copy_if brings the
+// positions to the buffer the host expects).
+__global__ void k_range_init(unsigned long long* range) { range[0] = 0xffffffffffffffffull; range[1] = 0ull; }
+__global__ void k_pass_flags(const unsigned long long* range, int* flags) {
+  const unsigned long long span = range[1] >= range[0] ? range[1] - range[0] : 0ull;
+  const int nbits = span ? 64 - __clzll((long long)span) : 0;
+  const int npass = (nbits + 7) / 8;
+  if (threadIdx.x < 8) flags[threadIdx.x] = (int)threadIdx.x < npass;
+  if (threadIdx.x == 8) flags[8] = npass & 1;
+}
+__global__ void k_copy_if(const unsigned* src, unsigned* dst, long long n, const int* flag) {
+  if (*flag == 0) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }
 __global__ void k_keys_of_positions(Indexer ix, long long n, const unsigned* pos, unsigned* keys) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1536,11 +1589,19 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
     // elements ordered by (group, value): sort by value key, then stably by group
     SortBufs b; b.k[0] = ws + L.k64[0]; b.k[1] = ws + L.k64[1]; b.v[0] = (unsigned*)(ws + L.v2[0]); b.v[1] = (unsigned*)(ws + L.v2[1]);
     b.hist = (unsigned*)(ws + L.hist); b.tile_sums = (unsigned*)(ws + L.tsum);
+    // integer values: sort (key - min) and skip the passes above bits(max - min) on the device (see k_pass_flags)
+    static const bool range_on = !(getenv("AGC_SORT_RANGE") && atoi(getenv("AGC_SORT_RANGE")) == 0);
+    const bool ranged = range_on && !dtype_is_float(r->a_dtype);
+    unsigned long long* range = (unsigned long long*)(ws + L.flag + 64);
+    int* pass_flags = (int*)(ws + L.flag + 128);
+    if (ranged) AGC_COUNT_LAUNCH(1), k_range_init<<<1, 1, 0, st>>>(range);
     AGC_COUNT_LAUNCH(1), k_value_keys<<<scan_grid(n, sms), 256, 0, st>>>(r->a, r->a_dtype, n, (r->flags & AGC_F_REVERSE) ? 1 : 0,
-                                                    (unsigned long long*)b.k[0], b.v[0]);
+                                                    (unsigned long long*)b.k[0], b.v[0], ranged ? range : nullptr);
+    if (ranged) AGC_COUNT_LAUNCH(1), k_pass_flags<<<1, 32, 0, st>>>(range, pass_flags);
     int lo_bit = 0;
     if (r->a_dtype == AGC_DT_F32) lo_bit = 24;              // f32 widened to f64: low 29 mantissa bits are zero
-    int res = radix_sort_pairs<unsigned long long>(b, 0, n, lo_bit, 64, nullptr, st);
+    int res = radix_sort_pairs<unsigned long long>(b, 0, n, lo_bit, 64, nullptr, st, ranged ? pass_flags : nullptr, ranged ? range : nullptr);
+    if (ranged) AGC_COUNT_LAUNCH(1), k_copy_if<<<scan_grid(n, sms), 256, 0, st>>>(b.v[res ^ 1], b.v[res], n, pass_flags + 8);
     // group keys of the value-ordered positions, then a stable sort by group
     SortBufs g; g.k[0] = ws + L.k32[0]; g.k[1] = ws + L.k32[1]; g.v[0] = b.v[res]; g.v[1] = b.v[res ^ 1];
     g.hist = b.hist; g.tile_sums = b.tile_sums;

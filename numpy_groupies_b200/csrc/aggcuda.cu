@@ -24,21 +24,25 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 int sm_count() { return agc::device_sms(); }                  // of the CURRENT device
 
-// measurement hook: one event pair per device (events belong to the device they were created on)
+// measurement hook: a ring of event pairs per device (events belong to the device they were created on), one pair per
+// agc_aggregate call -- a timed loop can run without reading anything back and collect the durations afterwards
 bool g_profile = false;
-struct ProfEvents { cudaEvent_t e0 = nullptr, e1 = nullptr; bool valid = false; };
+constexpr int PROF_RING = 64;
+struct ProfEvents { cudaEvent_t e0[PROF_RING] = {}, e1[PROF_RING] = {}; long long calls = 0; };
 ProfEvents g_prof[agc::AGC_MAX_DEVICES];
 int g_prof_last_dev = 0;
 void prof_begin(cudaStream_t st) {
   if (!g_profile) return;
   ProfEvents& pe = g_prof[agc::current_device()];
-  if (!pe.e0) { cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1); }
-  cudaEventRecord(pe.e0, st);
+  const int k = (int)(pe.calls % PROF_RING);
+  if (!pe.e0[k]) { cudaEventCreate(&pe.e0[k]); cudaEventCreate(&pe.e1[k]); }
+  cudaEventRecord(pe.e0[k], st);
 }
 void prof_end(cudaStream_t st) {
   if (!g_profile) return;
   const int dev = agc::current_device();
-  cudaEventRecord(g_prof[dev].e1, st); g_prof[dev].valid = true; g_prof_last_dev = dev;
+  ProfEvents& pe = g_prof[dev];
+  cudaEventRecord(pe.e1[pe.calls % PROF_RING], st); ++pe.calls; g_prof_last_dev = dev;
 }
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -231,7 +235,7 @@ int agc_aggregate(const agc_request_t* r, void* stream) {
   return 0;
 }
 
-int agc_profile_enable(int on) { g_profile = on != 0; for (auto& pe : g_prof) pe.valid = false; return 0; }
+int agc_profile_enable(int on) { g_profile = on != 0; for (auto& pe : g_prof) pe.calls = 0; return 0; }
 int agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_t* dst) {
   if (src_dtype != AGC_DT_I64 && src_dtype != AGC_DT_U64) return fail(-1, "agc_host_narrow_labels: 8-byte integer labels only");
   const unsigned long long* s = (const unsigned long long*)src;
@@ -241,14 +245,16 @@ int agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_
   }
   return 0;
 }
-float agc_profile_last_ms(void) {
+float agc_profile_ms(int back) {
   ProfEvents& pe = g_prof[g_prof_last_dev];
-  if (!pe.valid) return -1.f;
+  if (back < 0 || back >= PROF_RING || pe.calls - 1 - back < 0) return -1.f;
+  const int k = (int)((pe.calls - 1 - back) % PROF_RING);
   float ms = -1.f;
-  if (cudaEventSynchronize(pe.e1) != cudaSuccess) return -1.f;
-  cudaEventElapsedTime(&ms, pe.e0, pe.e1);
+  if (cudaEventSynchronize(pe.e1[k]) != cudaSuccess) return -1.f;
+  cudaEventElapsedTime(&ms, pe.e0[k], pe.e1[k]);
   return ms;
 }
+float agc_profile_last_ms(void) { return agc_profile_ms(0); }
 int64_t agc_launch_count(void) { return agc::g_launches.load(); }
 int agc_tuning(int key, int value) {
   agc::tuning_defaults();

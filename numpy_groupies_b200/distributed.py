@@ -222,10 +222,11 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
             _merge_owner_values(lib, req, plan.flat_size, group, device, stream)
         else:
             run(base_flags | _abi.F_FIN_ONLY)
-        if check:
+        if ac._want_check(c):                                    # (labels that already passed are remembered: aggregate_cuda._VALID)
             st = status.cpu()                                    # the only host synchronisation of the call
             if int(st[_abi.ST_BADLABEL]):
                 raise ValueError("group_idx contains negative indices or indices too large for size")
+            ac._mark_validated(c)
             ac._LAST["regime"] = int(st[_abi.ST_REGIME])
     if c.out_dtype != compute_out:
         out = ac._Dev(out.t.to(getattr(torch, c.out_dtype.name)), c.out_dtype)

@@ -341,3 +341,35 @@ def test_pageable_int64_labels_are_narrowed_on_the_way_to_the_device(func, monke
         g2[n // 3] = bad
         with pytest.raises(ValueError):
             aggregate(g2, a, func=func, size=groups)
+
+
+def test_validated_labels_are_remembered_until_they_change():
+    """check=True reads the status record back only until a CUDA label tensor has passed once for this size; any in-place
+    write (torch's version counter), another size, or another tensor object -- even at the same address -- is checked again."""
+    import torch
+    dev = torch.device("cuda")
+    n, groups = 1 << 16, 1000
+    g = torch.randint(0, groups, (n,), device=dev)
+    a = torch.rand(n, device=dev)
+    ac._VALID.clear()
+    ref = aggregate(g, a, func="sum", size=groups)
+    assert id(g) in ac._VALID
+    for _ in range(3):                                        # remembered: the same results, no read-back needed
+        torch.testing.assert_close(aggregate(g, a, func="sum", size=groups), ref)
+    torch.testing.assert_close(aggregate(g, a, func="sum", size=groups, check="always"), ref)
+    with pytest.raises(ValueError):                           # the same labels are NOT valid for a smaller size
+        aggregate(g, a, func="sum", size=groups // 2)
+    g[5] = groups + 7                                         # in-place write: version counter moves, checked again
+    with pytest.raises(ValueError):
+        aggregate(g, a, func="sum", size=groups)
+    with pytest.raises(ValueError):                           # and a tensor that failed is never remembered
+        aggregate(g, a, func="max", size=groups)
+    g[5] = 3
+    torch.testing.assert_close(aggregate(g, a, func="len", size=groups).sum().cpu(), torch.tensor(n))
+    del g
+    g2 = torch.full((n,), groups, device=dev, dtype=torch.int64)     # a new object (the allocator may hand out the same block)
+    with pytest.raises(ValueError):
+        aggregate(g2, a, func="sum", size=groups)
+    assert aggregate(g2, a, func="sum", size=groups, check=False).shape == (groups,)    # never checked, never remembered
+    with pytest.raises(ValueError):
+        aggregate(g2, a, func="sum", size=groups)

@@ -198,6 +198,27 @@ def test_sorted_label_scans_chained_kernel(n, groups):
     np.testing.assert_array_equal(aggregate(g2, a, func="cumsum", size=groups), oracle.aggregate(g2, a, func="cumsum", size=groups))
 
 
+@pytest.mark.parametrize("dtype,lo,hi", [(np.int64, 7, 8), (np.int64, -100, 100), (np.int64, -35000, 35000), (np.int64, -2**31, 2**31),
+                                         (np.int64, -2**62, 2**62), (np.int32, -2**20, 2**20), (np.uint16, 0, 65536), (np.int8, -128, 128), (np.uint64, 2**63 - 5, 2**63 + 500)])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_sort_with_range_compressed_value_keys(dtype, lo, hi, reverse):
+    """func='sort' on integer values sorts (key - min) and skips, on the device, the radix passes above bits(max - min):
+    0 passes (all equal), 1, 3 (odd: the positions change buffers once more), 4, 8; ties keep their order (stable).
+    reverse=True sorts -a as numpy computes it: the negation wraps in the array's own width, so 0 of an unsigned type and the
+    most negative value of a signed one stay in front (uint16 with zeros, int8 with -128)."""
+    rng = np.random.default_rng(5)
+    n, groups = (1 << 20) + 321, 3000
+    gidx = rng.integers(0, groups, n)
+    if dtype == np.uint64:
+        a = (rng.integers(0, hi - lo, n).astype(np.uint64) + np.uint64(lo))
+    else:
+        a = rng.integers(lo, hi, n).astype(dtype)
+    got = aggregate(gidx, a, func="sort", size=groups, reverse=reverse)
+    ref = oracle.aggregate(gidx, a, func="sort", size=groups, reverse=reverse)
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
+
+
 @pytest.mark.parametrize("func", ["first", "last", "argmax", "argmin", "nanargmax", "any", "all", "prod", "nanfirst"])
 def test_other_reductions_f64(func):
     rng = np.random.default_rng(31)
@@ -340,7 +361,7 @@ def test_large_table_kernels_full_size_agree():
         for mode in (3, 4, 0):
             ac.tuning(large=mode)
             for func in ("sum", "mean", "max", "min", "len"):
-                res[mode, func] = aggregate(gidx, a, func=func, size=groups)
+                res[mode, func] = aggregate(gidx, a, func=func, size=groups, check="always")   # (the regime travels in the status record)
                 assert (ac.last_regime() // 10) == {3: 1, 4: 5, 0: 2}[mode], (mode, func, ac.last_regime())
     finally:
         ac.tuning(large=1)
@@ -464,7 +485,7 @@ def test_sorted_labels_full_size_run_kernel():
         for mode in (1, 0):
             ac.tuning(large=mode)
             for func in ("sum", "mean", "max", "len"):
-                res[mode, func] = aggregate(gidx, a, func=func, size=groups)
+                res[mode, func] = aggregate(gidx, a, func=func, size=groups, check="always")
                 assert (ac.last_regime() // 10) == (5 if mode == 1 else 2), (mode, func, ac.last_regime())
     finally:
         ac.tuning(large=1)
