@@ -240,12 +240,12 @@ def run_reference(args):
     best_name = min(res, key=res.get)
     dt = res[best_name]
     val = n / dt * 1e-9
-    cfg = workload_config(args)
-    cfg["reference_sample"] = f"each timed step aggregates N=2^{log2n} elements drawn like the workload's (bounded CPU sample)"
+    cfg = workload_config(args)                              # the very dict the GPU arm prints (the sample size is in cpu_baseline.sample)
     line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": "Gelem/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
+            "reference_sample": f"each timed step aggregates N=2^{log2n} elements drawn like the workload's (bounded CPU sample)",
             "backend": best_name,
             "backends_gelem_s": {k: n / v * 1e-9 for k, v in res.items()},
             "cpu_baseline": {"value": val, "unit": "Gelem/s", "cores": 1, "kind": kind,
