@@ -379,6 +379,10 @@ def run_other_config(args):
                          "traffic": None, "peak_source": peak_src, "kernel_ms": ms_head, "algorithmic_bytes": head_bytes,
                          "kernel": "whole call (several kernels), CUDA events around the public API call"},
             "gpu_launches": int(launches), "points": points}
+    del a
+    torch.cuda.empty_cache()
+    if getattr(args, "_embed", False):
+        return line
     print(json.dumps(line), flush=True)
 
 
@@ -624,6 +628,19 @@ def main():
 
     del labels, a
     torch.cuda.empty_cache()
+    # ---- the other BASELINE.json configurations (C3 f64 / 10^6 groups, C4 N -> N and sort, C5 Forms 3 and 4), one GPU: a few
+    #      steps each, so that the driver's own run of this file carries them too (`--config C3|C4|C5` prints them alone) ------
+    if world == 1 and not args.no_sweep:
+        others = {}
+        for cfg in ("C3", "C4", "C5"):
+            try:
+                sub = argparse.Namespace(**vars(args))
+                sub.config, sub.steps, sub.warmup, sub._embed = cfg, 3, 3, True
+                o = run_other_config(sub)
+                others[cfg] = {"workload": o["config"]["workload"], "points": o["points"]}
+            except Exception as e:                            # noqa: BLE001
+                others[cfg] = {"error": str(e)[:200]}
+        line["other_configs"] = others
     try:
         line["cpu_baseline"] = cpu_baseline_block(args.func, G, args.dist, args.cpu_log2n or 26)
     except Exception as e:                                    # noqa: BLE001

@@ -12,7 +12,8 @@ timeout 900 python bench.py --steps 20 --warmup 3 > $O/bench.json 2> $O/bench.er
 python - "$O" <<'PY'
 import json, sys
 d=json.loads(open(sys.argv[1]+"/bench.json").read().strip().splitlines()[-1])
-print("value", round(d["value"],1), "ms", round(d["ms_per_step"],3), "frac", round(d["roofline"]["frac"],4), "verified", d["verified"].get("ok"), "e2e", d.get("e2e"))
+print("value", round(d["value"],1), "ms", round(d["ms_per_step"],3), "frac", round(d["roofline"]["frac"],4), "verified", d["verified"].get("ok"), "always", d.get("value_check_always"), "false", d.get("value_check_false"), "e2e", d.get("e2e"))
+print({k: [(p.get("func"), p.get("sorted", p.get("form", "")), p.get("ms")) for p in v.get("points", [])] for k, v in d.get("other_configs", {}).items()})
 for s in d.get("sweep", []): print("  ", s)
 PY
 tail -3 $O/bench.err
@@ -24,8 +25,7 @@ print(sys.argv[1], round(d["roofline"]["frac"],3)); [print("   ", p) for p in d.
 PY
 done
 timeout 300 python scripts/r2_scan_bench.py 28 2> $O/scan.err | grep '"chain": 1' > $O/scan_ws.jsonl; cat $O/scan_ws.jsonl | cut -c1-160
-AGC_SCAN_WS=0 timeout 300 python scripts/r2_scan_bench.py 28 2>> $O/scan.err | grep '"chain": 1' > $O/scan_pipe.jsonl
-AGC_SCAN_PIPE=0 timeout 300 python scripts/r2_scan_bench.py 28 2>> $O/scan.err | grep '"chain": 1' > $O/scan_lean.jsonl
+AGC_SCAN_WS=0 timeout 300 python scripts/r2_scan_bench.py 28 2>> $O/scan.err | grep '"chain": 1' > $O/scan_lean.jsonl
 timeout 300 python bench.py --steps 2 --warmup 1 --no-sweep --no-e2e > $O/plain_small.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-sweep --no-e2e > $O/ncu_launches.log 2>&1
 tail -1 $O/ncu_launches.log
