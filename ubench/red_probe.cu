@@ -249,6 +249,52 @@ __global__ void __launch_bounds__(1024, 1) k_spill2(const unsigned short* __rest
   for (int i = threadIdx.x; i < nup; i += blockDim.x) if (su[i]) red_f64(tab + cov + i, (double)su[i]);
 }
 
+
+// "atoms + red" with the VALUES fetched by cp.async (LDGSTS.cg: global -> shared memory, no L1 line behind the bytes in
+// flight) into one 16-byte slot per thread; the labels keep coming through the L1.  Question: with the 228 KB carve-out the
+// L1 holds 28 KB of loads in flight -- does taking a third of the traffic out of it lift the streaming rate?
+__global__ void __launch_bounds__(1024, 1) k_red_ldgsts(const long long* __restrict__ idx, const float* __restrict__ a, long long n, double* tab, int cov) {
+  extern __shared__ unsigned su[];
+  int4* ring = reinterpret_cast<int4*>(su + cov) + threadIdx.x;        // (cov is a multiple of 4: 16-byte aligned)
+  for (int i = threadIdx.x; i < cov; i += blockDim.x) su[i] = 0u;
+  __syncthreads();
+  const unsigned rs = (unsigned)__cvta_generic_to_shared(ring);
+  const long long nvec = n >> 2, per = (nvec + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * per, v1 = v0 + per < nvec ? v0 + per : nvec;
+  int4 l0 = make_int4(0, 0, 0, 0), l1 = l0;
+  long long v = v0 + threadIdx.x;
+  if (v < v1) {
+    l0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v);
+    l1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v + 1);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rs), "l"(reinterpret_cast<const int4*>(a) + v) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (long long vb = v0; vb < v1; vb += blockDim.x) {
+    const bool live = v < v1;
+    const long long vn = v + blockDim.x;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int4 av = *ring;                                             // this thread's own slot: no barrier needed
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+    if (vn < v1) {
+      n0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * vn);
+      n1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * vn + 1);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(rs), "l"(reinterpret_cast<const int4*>(a) + vn) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int g4[4] = {l0.x, l0.z, l1.x, l1.z};
+    const int x4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!live) continue;
+      if (g4[j] < cov) atomicAdd(&su[g4[j]], (unsigned)x4[j] >> 20);
+      else red_f64(tab + g4[j], (double)__int_as_float(x4[j]));
+    }
+    l0 = n0; l1 = n1; v = vn;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cov; i += blockDim.x) if (su[i]) red_f64(tab + i, (double)su[i]);
+}
+
 template <class L> static double time_ms(L launch, int warm = 2, int reps = 5) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int i = 0; i < warm; ++i) launch();
@@ -319,6 +365,14 @@ int main(int argc, char** argv) {
     CK(cudaFuncSetAttribute((const void*)k_red1b, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX - 1024));
     double ms1b = time_ms([&] { k_spill1b<<<sms, 1024, 199552>>>(idx, a, N, tab, cov, rslot, rval, rcount, cap); });
     double msr = time_ms([&] { k_red1b<<<sms, 1024, 199552>>>(idx, a, N, tab, cov); });
+    CK(cudaFuncSetAttribute((const void*)k_red_ldgsts, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX - 1024));
+    for (int big = 0; big < 2; ++big) {
+      const int smem = big ? 231424 : 199552;
+      const int covl = ((smem - 16384) / 4) & ~3, covp = (smem / 4) & ~3;
+      double m_plain = time_ms([&] { k_red1b<<<sms, 1024, smem>>>(idx, a, N, tab, covp); });
+      double m_ldgsts = time_ms([&] { k_red_ldgsts<<<sms, 1024, smem>>>(idx, a, N, tab, covl); });
+      printf("{\"mode\": \"values by cp.async into a 16 KB ring\", \"smem\": %d, \"cov_plain\": %d, \"plain_ms\": %.3f, \"cov_ring\": %d, \"ring_ms\": %.3f}\n", smem, covp, m_plain, covl, m_ldgsts);
+    }
     printf("{\"mode\": \"prefetched skeleton\", \"spill_pass1_ms\": %.3f, \"atoms_red_ms\": %.3f}\n", ms1b, msr);
     printf("{\"mode\": \"atoms + spilled records (u16 slot, f32), replay kernel\", \"cov\": %d, \"pass1_ms\": %.3f, \"pass2_ms\": %.3f, \"both_ms\": %.3f, \"gelem_s\": %.1f}\n",
            cov, ms1, ms2, both, N / both * 1e-6);
