@@ -184,6 +184,8 @@ _STAGE_BUFS = 3
 # host threads that fill the staging buffers (memcpy / label narrowing release the GIL): half the cores, at most 8
 _STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(2, min(8, (os.cpu_count() or 4) // 2))
 _NARROW_LABELS = os.environ.get("AGC_NARROW_LABELS", "1") != "0"
+# arrays of at least this many bytes go through the staging ring / as one asynchronous DMA; smaller ones as a plain copy
+_STAGE_MIN = int(os.environ.get("AGC_STAGE_MIN", 8 << 20))
 
 
 def _stage_setup():
@@ -278,7 +280,7 @@ def _upload(arr, device):
         except ValueError:
             view = np.array(view)
     t = torch.from_numpy(view)
-    if view.nbytes >= (8 << 20):
+    if view.nbytes >= _STAGE_MIN:
         if t.is_pinned():
             return _Dev(t.to(device, non_blocking=True), dt)
         with torch.cuda.device(device):
@@ -533,7 +535,7 @@ def _labels_on_device(c, device):
             # touch every byte anyway); page-locked arrays go as they are, one DMA (narrowing them measured slower: the
             # host threads move 37 GB/s here, the link 54)
             if (_NARROW_LABELS and plan is not None and plan.form == "flat" and not plan.needs_size and 0 < plan.flat_size < 2 ** 31
-                    and g.dtype.kind in "iu" and g.dtype.itemsize == 8 and g.nbytes >= (8 << 20) and not _is_pinned_np(g)):
+                    and g.dtype.kind in "iu" and g.dtype.itemsize == 8 and g.nbytes >= _STAGE_MIN and not _is_pinned_np(g)):
                 c._labels_dev = _upload_labels_narrowed(g, device)
             else:
                 c._labels_dev = _upload(g, device)
