@@ -205,6 +205,9 @@ int         agc_owner_pack(const agc_request_t* req, int64_t* carrier, int32_t u
  * staging buffer -- mapping every label outside [0, 2^31) to -1, which the kernels report as a bad label exactly like
  * the original value.  Pure host code, thread-safe, no CUDA call; callers run it on slices from several threads. */
 int         agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_t* dst);
+/* The same staging step for everything else: a copy with non-temporal stores (the destination is read next by the DMA engine,
+ * not by this core: no read-for-ownership, no cache pollution). */
+int         agc_host_copy_stream(const void* src, void* dst, int64_t bytes);
 
 /* measurement hooks (bench.py): when enabled, agc_aggregate brackets its dominant accumulate kernel with
  * CUDA events on the caller's stream -- a ring of 64 pairs, one per call, so a timed loop needs no read-back;

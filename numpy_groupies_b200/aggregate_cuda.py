@@ -184,6 +184,7 @@ _STAGE_BUFS = 3
 # host threads that fill the staging buffers (memcpy / label narrowing release the GIL): half the cores, at most 8
 _STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(2, min(8, (os.cpu_count() or 4) // 2))
 _NARROW_LABELS = os.environ.get("AGC_NARROW_LABELS", "1") != "0"
+_NARROW_PINNED = os.environ.get("AGC_NARROW_PINNED", "0") != "0"      # page-locked labels too (measured slower than their plain DMA)
 # arrays of at least this many bytes go through the staging ring / as one asynchronous DMA; smaller ones as a plain copy
 _STAGE_MIN = int(os.environ.get("AGC_STAGE_MIN", 8 << 20))
 
@@ -229,7 +230,9 @@ def _stage_ring(n_items, item_bytes, fill, dst_u8):
 def _upload_staged(src_u8, dst_u8):
     """Pageable host bytes -> device at close to PCIe rate.  (A plain copy from pageable memory runs at ~14 GB/s: the
     driver stages it through one small buffer, single-threaded.)"""
-    _stage_ring(src_u8.shape[0], 1, lambda stage, lo, hi: np.copyto(stage, src_u8[lo:hi]), dst_u8)
+    lib = _abi.load()
+    base = src_u8.ctypes.data
+    _stage_ring(src_u8.shape[0], 1, lambda stage, lo, hi: lib.agc_host_copy_stream(base + lo, stage.ctypes.data, hi - lo), dst_u8)
 
 
 def _is_pinned_np(arr):
@@ -535,7 +538,7 @@ def _labels_on_device(c, device):
             # touch every byte anyway); page-locked arrays go as they are, one DMA (narrowing them measured slower: the
             # host threads move 37 GB/s here, the link 54)
             if (_NARROW_LABELS and plan is not None and plan.form == "flat" and not plan.needs_size and 0 < plan.flat_size < 2 ** 31
-                    and g.dtype.kind in "iu" and g.dtype.itemsize == 8 and g.nbytes >= _STAGE_MIN and not _is_pinned_np(g)):
+                    and g.dtype.kind in "iu" and g.dtype.itemsize == 8 and g.nbytes >= _STAGE_MIN and (_NARROW_PINNED or not _is_pinned_np(g))):
                 c._labels_dev = _upload_labels_narrowed(g, device)
             else:
                 c._labels_dev = _upload(g, device)

@@ -7,6 +7,7 @@
 #include "agc_generic.cuh"
 #include "agc_small.cuh"
 #include "agc_fast.cuh"
+#include <emmintrin.h>
 #include "agc_dispatch.cuh"
 #include "agc_scan.cuh"
 #include "agc_labels.cuh"
@@ -239,10 +240,39 @@ int agc_profile_enable(int on) { g_profile = on != 0; for (auto& pe : g_prof) pe
 int agc_host_narrow_labels(const void* src, int32_t src_dtype, int64_t n, int32_t* dst) {
   if (src_dtype != AGC_DT_I64 && src_dtype != AGC_DT_U64) return fail(-1, "agc_host_narrow_labels: 8-byte integer labels only");
   const unsigned long long* s = (const unsigned long long*)src;
-  for (int64_t i = 0; i < n; ++i) {                       // branch-free: vectorises
-    const unsigned long long v = s[i];
-    dst[i] = (v >> 31) ? -1 : (int32_t)v;
+  int64_t i = 0;
+  auto one = [&](int64_t k) { const unsigned long long v = s[k]; dst[k] = (v >> 31) ? -1 : (int32_t)v; };
+  // The staging threads are bound by the host's memory system, not by arithmetic: non-temporal stores keep the destination
+  // (a page-locked buffer the DMA engine reads next) out of the caches and spare the read-for-ownership of every line --
+  // 12 instead of 16 bytes of DRAM traffic per label.
+  while (i < n && ((uintptr_t)(dst + i) & 15)) one(i++);
+  const __m128i zero = _mm_setzero_si128();
+  for (; i + 8 <= n; i += 8) {
+    const __m128 a0 = _mm_castsi128_ps(_mm_loadu_si128((const __m128i*)(s + i))), a1 = _mm_castsi128_ps(_mm_loadu_si128((const __m128i*)(s + i + 2)));
+    const __m128 b0 = _mm_castsi128_ps(_mm_loadu_si128((const __m128i*)(s + i + 4))), b1 = _mm_castsi128_ps(_mm_loadu_si128((const __m128i*)(s + i + 6)));
+    const __m128i lo0 = _mm_castps_si128(_mm_shuffle_ps(a0, a1, 0x88)), hi0 = _mm_castps_si128(_mm_shuffle_ps(a0, a1, 0xDD));
+    const __m128i lo1 = _mm_castps_si128(_mm_shuffle_ps(b0, b1, 0x88)), hi1 = _mm_castps_si128(_mm_shuffle_ps(b0, b1, 0xDD));
+    const __m128i ok0 = _mm_cmpeq_epi32(_mm_or_si128(hi0, _mm_srai_epi32(lo0, 31)), zero);      // label in [0, 2^31)
+    const __m128i ok1 = _mm_cmpeq_epi32(_mm_or_si128(hi1, _mm_srai_epi32(lo1, 31)), zero);
+    _mm_stream_si128((__m128i*)(dst + i), _mm_or_si128(_mm_and_si128(lo0, ok0), _mm_andnot_si128(ok0, _mm_set1_epi32(-1))));
+    _mm_stream_si128((__m128i*)(dst + i + 4), _mm_or_si128(_mm_and_si128(lo1, ok1), _mm_andnot_si128(ok1, _mm_set1_epi32(-1))));
   }
+  for (; i < n; ++i) one(i);
+  _mm_sfence();
+  return 0;
+}
+int agc_host_copy_stream(const void* src, void* dst, int64_t bytes) {
+  const char* s = (const char*)src; char* d = (char*)dst;
+  int64_t i = 0;
+  while (i < bytes && ((uintptr_t)(d + i) & 15)) { d[i] = s[i]; ++i; }
+  for (; i + 64 <= bytes; i += 64) {
+    const __m128i v0 = _mm_loadu_si128((const __m128i*)(s + i)), v1 = _mm_loadu_si128((const __m128i*)(s + i + 16));
+    const __m128i v2 = _mm_loadu_si128((const __m128i*)(s + i + 32)), v3 = _mm_loadu_si128((const __m128i*)(s + i + 48));
+    _mm_stream_si128((__m128i*)(d + i), v0); _mm_stream_si128((__m128i*)(d + i + 16), v1);
+    _mm_stream_si128((__m128i*)(d + i + 32), v2); _mm_stream_si128((__m128i*)(d + i + 48), v3);
+  }
+  for (; i < bytes; ++i) d[i] = s[i];
+  _mm_sfence();
   return 0;
 }
 float agc_profile_ms(int back) {
