@@ -1342,6 +1342,14 @@ __global__ void k_sort_place(const void* a, int eb, long long n, const unsigned*
     }
   }
 }
+__global__ void k_gather_by_pos(const void* a, int eb, long long n, const unsigned* src_pos, void* staged) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned s = src_pos[i];
+    if (eb == 8) ((unsigned long long*)staged)[i] = ((const unsigned long long*)a)[s];
+    else ((unsigned*)staged)[i] = ((const unsigned*)a)[s];
+  }
+}
 __global__ void k_order_widen(const unsigned* p0, const unsigned* p1, const int* unsorted, long long n, long long* order) {
   const unsigned* pos = *unsorted ? p1 : p0;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1607,7 +1615,20 @@ inline int run_scan_op(const agc_request_t* r, cudaStream_t st, int sms) {
     g.hist = b.hist; g.tile_sums = b.tile_sums;
     AGC_COUNT_LAUNCH(1), k_keys_of_positions<<<scan_grid(n, sms), 256, 0, st>>>(ix, n, g.v[0], (unsigned*)g.k[0]);
     int res2 = radix_sort_pairs<unsigned>(g, 0, n, 0, bits_for(r->size), nullptr, st);
-    AGC_COUNT_LAUNCH(1), k_sort_place<<<scan_grid(n, sms), 256, 0, st>>>(r->a, dtype_bytes(r->a_dtype), n, slot, g.v[res2], r->out);
+    // placement out[slot[i]] = a[src[i]]: for large inputs the gather goes to a staging buffer in sorted order (the value-key
+    // buffers are free by now) and the window un-sort brings the values home, instead of a random gather AND a random scatter
+    // per element (20 ms of the 62 at N = 2^28)
+    const int ebs = dtype_bytes(r->a_dtype);
+    static const bool win = !(getenv("AGC_UNSORT_WINDOW") && atoi(getenv("AGC_UNSORT_WINDOW")) == 0);
+    if (win && n >= (1ll << 22) && (ebs == 8 || ebs == 4)) {
+      void* stage = ws + L.k64[0]; void* val_part = ws + L.k64[1];
+      unsigned* pos_part = (unsigned*)g.k[res2 ^ 1];           // the key buffer of the group sort that does not hold its result
+      AGC_COUNT_LAUNCH(1), k_gather_by_pos<<<scan_grid(n, sms), 256, 0, st>>>(r->a, ebs, n, g.v[res2], stage);
+      if (ebs == 8) unsort_windowed<unsigned long long>(slot, (const unsigned long long*)stage, n, (unsigned long long*)r->out, pos_part, (unsigned long long*)val_part, g.hist, g.tile_sums, nullptr, st);
+      else unsort_windowed<unsigned>(slot, (const unsigned*)stage, n, (unsigned*)r->out, pos_part, (unsigned*)val_part, g.hist, g.tile_sums, nullptr, st);
+      return 0;
+    }
+    AGC_COUNT_LAUNCH(1), k_sort_place<<<scan_grid(n, sms), 256, 0, st>>>(r->a, ebs, n, slot, g.v[res2], r->out);
     return 0;
   }
   p.keys[0] = keys[0]; p.keys[1] = keys[1]; p.pos[0] = pos[0]; p.pos[1] = pos[1]; p.unsorted = flag;
