@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-.}"
-O=gpurun_out/r2dist8b; mkdir -p $O
+O=gpurun_out/r2dist8; mkdir -p $O
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py > $O/check_8_final.log 2>&1
 tail -2 $O/check_8_final.log | cut -c1-200
 for sc in weak strong; do
