@@ -1019,7 +1019,8 @@ constexpr int WS_THREADS = SG_THREADS + 32;
 constexpr int WS_SMEM = 115712;                                   // two CTAs per SM: (228 KB - 2 * 1 KB reserved) / 2; 496 B of small state + alignment + 7 tile buffers
 __device__ __forceinline__ void sp_mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
-template <class A, int OP, int VK, bool NANSKIP>
+// LB: bytes per label (8: int64, 4: int32 -- rows of 32 bytes with the 32-byte swizzle: unit k of row t sits at k ^ ((t >> 2) & 1))
+template <class A, int OP, int VK, bool NANSKIP, int LB>
 __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams p, unsigned long long* desc, int nfull,
                                                                const __grid_constant__ CUtensorMap tm_lab, const __grid_constant__ CUtensorMap tm_val,
                                                                const __grid_constant__ CUtensorMap tm_out32) {
@@ -1045,10 +1046,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams 
   const unsigned sleep_ns = (unsigned)p.lb_sleep & 0xffffu; const bool gpu_scope = (p.lb_sleep >> 30) & 1;
   auto issue = [&](int s, int tile) {
     const unsigned bar = bar_full + 8 * s;
-    sp_expect_tx(bar, 2 * SP_IN_BYTES + (tile > 0 ? 16 : 0));
+    sp_expect_tx(bar, SG_TILE * LB + SP_IN_BYTES + (tile > 0 ? 16 : 0));
     sp_tensor_load(sp_saddr(s_in + (2 * s) * (SG_TILE / 2)), &tm_lab, tile * SG_THREADS, bar);
     sp_tensor_load(sp_saddr(s_in + (2 * s + 1) * (SG_TILE / 2)), &tm_val, tile * SG_THREADS, bar);
-    if (tile > 0) sp_bulk_load(sp_saddr(s_left + s), (const long long*)p.labels + (long long)tile * SG_TILE - 2, 16, bar);
+    if (tile > 0) sp_bulk_load(sp_saddr(s_left + s), (const char*)p.labels + ((long long)tile * SG_TILE) * LB - 16, 16, bar);
   };
   if (t == SG_THREADS) {                                                 // lane 0 of the ninth warp sets everything up
 #pragma unroll
@@ -1150,14 +1151,26 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams 
     const int s = it % SP_STAGES, slot = it & 1;
     sp_mbar_wait(bar_full + 8 * s, (unsigned)(it / SP_STAGES) & 1u);
     unsigned long long gl[SG_ITEMS], raw[SG_ITEMS];
-    sp_read8(s_in + (2 * s) * (SG_TILE / 2), t, gl);
+    const int4* lab_s = s_in + (2 * s) * (SG_TILE / 2);
+    if (LB == 8) sp_read8(lab_s, t, gl);
+    else {
+      const int r1 = (t >> 2) & 1;
+      const int4 u0 = lab_s[2 * t + r1], u1 = lab_s[2 * t + (1 ^ r1)];
+      gl[0] = (unsigned long long)(long long)u0.x; gl[1] = (unsigned long long)(long long)u0.y; gl[2] = (unsigned long long)(long long)u0.z; gl[3] = (unsigned long long)(long long)u0.w;
+      gl[4] = (unsigned long long)(long long)u1.x; gl[5] = (unsigned long long)(long long)u1.y; gl[6] = (unsigned long long)(long long)u1.z; gl[7] = (unsigned long long)(long long)u1.w;
+    }
     sp_read8(s_in + (2 * s + 1) * (SG_TILE / 2), t, raw);
     const long long base = (long long)tile * SG_TILE + (long long)t * SG_ITEMS;
     long long prev = 0;
     const long long left = __shfl_up_sync(0xffffffffu, (long long)gl[SG_ITEMS - 1], 1);
     if (lane > 0) prev = left;
-    else if (t > 0) { const int4 q = (s_in + (2 * s) * (SG_TILE / 2))[4 * (t - 1) + (3 ^ (((t - 1) >> 1) & 3))]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
-    else if (tile > 0) { const int4 q = s_left[s]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
+    else if (t > 0) {                                                    // the last label of the row before this thread's
+      if (LB == 8) { const int4 q = lab_s[4 * (t - 1) + (3 ^ (((t - 1) >> 1) & 3))]; prev = (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)); }
+      else { const int4 q = lab_s[2 * (t - 1) + (1 ^ (((t - 1) >> 2) & 1))]; prev = (long long)q.w; }
+    } else if (tile > 0) {
+      const int4 q = s_left[s];
+      prev = LB == 8 ? (long long)(((unsigned long long)(unsigned)q.z) | ((unsigned long long)(unsigned)q.w << 32)) : (long long)q.w;
+    }
     A x[SG_ITEMS]; unsigned hmask = 0;
     A tx = A(0); bool uns = false, bad = false;
 #pragma unroll
@@ -1458,14 +1471,16 @@ inline sp_encode_fn sp_encoder() {
   }();
   return fn;
 }
-inline bool sp_tile_map(CUtensorMap* tm, const void* base, int nfull, int box_rows = SG_THREADS) {
+inline bool sp_tile_map(CUtensorMap* tm, const void* base, int nfull, int box_rows = SG_THREADS, int elem_bytes = 8) {
   sp_encode_fn enc = sp_encoder();
   if (!enc || nfull <= 0) return false;
+  // rows of 8 elements: 64 bytes with the 64-byte swizzle for 8-byte elements, 32 bytes with the 32-byte swizzle for int32 labels
   const cuuint64_t dims[2] = {8, (cuuint64_t)nfull * SG_THREADS};
-  const cuuint64_t strides[1] = {64};
+  const cuuint64_t strides[1] = {(cuuint64_t)(8 * elem_bytes)};
   const cuuint32_t box[2] = {8, (cuuint32_t)box_rows}, estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return enc(tm, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, elem_bytes == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 template <class A, int OP, class LT>
 inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, cudaStream_t st) {
@@ -1484,7 +1499,8 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
       const bool ints = std::is_same<A, long long>::value && (i64v || u64v) && (p.out_dtype == AGC_DT_I64 || p.out_dtype == AGC_DT_U64);
       const bool flts = std::is_same<A, double>::value && f64v && p.out_dtype == AGC_DT_F64 && (OP == SC_SUM || OP == SC_PROD);
       static const bool lean_on = !(getenv("AGC_SCAN_LEAN") && atoi(getenv("AGC_SCAN_LEAN")) == 0);
-      if (lean_on && sizeof(LT) == 8 && (ints || flts) && !((uintptr_t)p.a & 15) && !((uintptr_t)p.out & 15)) {
+      constexpr int LBYTES = (int)sizeof(LT);                // int64 or int32 labels; the one-tile-per-CTA fallback takes int64 only
+      if (lean_on && (ints || flts) && !((uintptr_t)p.a & 15) && !((uintptr_t)p.out & 15)) {
         nfull = (int)(p.n / SG_TILE);
         if (nfull > 0) {
           unsigned long long* d = (unsigned long long*)(ws + L.desc);
@@ -1494,27 +1510,28 @@ inline void run_seg_scan_direct(const ScanParams& p, char* ws, const ScanWs& L, 
           static const int occ = getenv("AGC_SCAN_OCC") ? atoi(getenv("AGC_SCAN_OCC")) : 6;
           static const bool ws_on = !(getenv("AGC_SCAN_WS") && atoi(getenv("AGC_SCAN_WS")) == 0);
           CUtensorMap tml, tmv, tmo32;                           // tiles of 256 rows x 64 bytes (64-byte swizzle); tmo32: one warp's 32 rows of the result
-          const bool ws_ok = ws_on && sp_tile_map(&tml, p.labels, nfull) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo32, p.out, nfull, 32);
+          const bool ws_ok = ws_on && sp_tile_map(&tml, p.labels, nfull, SG_THREADS, LBYTES) && sp_tile_map(&tmv, p.a, nfull) && sp_tile_map(&tmo32, p.out, nfull, 32);
           // cooperative launch: the runtime refuses a grid that cannot be resident as a whole (then the one-tile-per-CTA kernel
           // runs) and never starts part of it -- the round-robin tile order of the kernel depends on exactly that
 #define AGC_PIPE(VK_, NS_)                                                                                              \
           { static std::atomic<unsigned long long> attr_done{0};                                                           \
             int per_sm = 0;                                                                                                \
-            if (ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_>, WS_SMEM, attr_done))                                       \
-              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_ws<A, OP, VK_, NS_>, WS_THREADS, WS_SMEM);  \
+            if (ensure_dyn_smem(k_seg_scan_ws<A, OP, VK_, NS_, LBYTES>, WS_SMEM, attr_done))                                       \
+              cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_scan_ws<A, OP, VK_, NS_, LBYTES>, WS_THREADS, WS_SMEM); \
             const long long cap = (long long)per_sm * device_sms();                                                        \
             const int pgrid = (int)(nfull < cap ? nfull : cap);                                                            \
             launched = false;                                                                                              \
             if (pgrid > 0) {                                                                                               \
               ScanParams pa = p; unsigned long long* da = d; int nf = nfull;                                               \
               void* args[] = {&pa, &da, &nf, &tml, &tmv, &tmo32};                                                          \
-              launched = cudaLaunchCooperativeKernel((const void*)k_seg_scan_ws<A, OP, VK_, NS_>, dim3(pgrid), dim3(WS_THREADS), args, WS_SMEM, st) == cudaSuccess; \
+              launched = cudaLaunchCooperativeKernel((const void*)k_seg_scan_ws<A, OP, VK_, NS_, LBYTES>, dim3(pgrid), dim3(WS_THREADS), args, WS_SMEM, st) == cudaSuccess; \
               if (!launched) cudaGetLastError();                                                                           \
             } }
 #define AGC_LEAN(VK_, NS_)                                                                                              \
           { bool launched = ws_ok;                                                                                         \
             if (ws_ok) AGC_PIPE(VK_, NS_)                                                                                  \
             if (launched) {}                                                                                               \
+            else if (LBYTES != 8) nfull = 0;                       /* int32 labels: the general chained kernel takes every tile */ \
             else if (occ == 5) k_seg_scan_lean<A, OP, VK_, NS_, 5><<<nfull, SG_THREADS, 0, st>>>(p, d);                     \
             else k_seg_scan_lean<A, OP, VK_, NS_, 6><<<nfull, SG_THREADS, 0, st>>>(p, d); }
           if (flts) { if (ns) AGC_LEAN(2, true) else AGC_LEAN(2, false) }

@@ -36,6 +36,10 @@ def timeit_batched(fn, k=20):
     return e0.elapsed_time(e1) / k
 
 
+lab32 = lab.to(torch.int32)
+ms32 = timeit_batched(lambda: aggregate(lab32, a, func="cumsum", size=G, check=False))
+print(json.dumps({"func": "cumsum", "dtype": "torch.int64", "labels": "int32", "log2n": log2n, "ms_back_to_back": round(ms32, 3),
+                  "frac_of_peak": round(n * 20 / ms32 * 1e-6 / peak, 4), "equal_to_int64_labels": bool(torch.equal(aggregate(lab32, a, func="cumsum", size=G), aggregate(lab, a, func="cumsum", size=G)))}), flush=True)
 ref = {}
 for chain in (0, 1):
     ac.tuning(scan_chain=chain)

@@ -177,6 +177,9 @@ def test_sorted_label_scans_chained_kernel(n, groups):
         np.testing.assert_array_equal(aggregate(gidx, a, func=func, size=groups), oracle.aggregate(gidx, a, func=func, size=groups))
     small = rng.integers(-2, 3, n)
     np.testing.assert_array_equal(aggregate(gidx, small, func="cumprod", size=groups), oracle.aggregate(gidx, small, func="cumprod", size=groups))
+    g32 = gidx.astype(np.int32)                              # int32 labels: 32-byte rows, the 32-byte swizzle
+    for func in ("cumsum", "cummin"):
+        np.testing.assert_array_equal(aggregate(g32, a, func=func, size=groups), oracle.aggregate(gidx, a, func=func, size=groups))
     u = rng.integers(0, 2**63, n).astype(np.uint64) * np.uint64(2) + np.uint64(1)          # values above 2^63: the order-preserving key matters
     for func in ("cummax", "cummin"):
         got = aggregate(gidx, u, func=func, size=groups)
