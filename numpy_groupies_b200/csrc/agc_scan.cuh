@@ -964,9 +964,11 @@ __device__ __forceinline__ void sp_write8(int4* buf, int t, const unsigned long 
     buf[4 * t + (j ^ r)] = make_int4((int)(unsigned)in[2 * j], (int)(in[2 * j] >> 32), (int)(unsigned)in[2 * j + 1], (int)(in[2 * j + 1] >> 32));
 }
 // look-back with the first window's descriptors already requested (m, xb)
-template <class A, int OP>
+struct SpNoHook { __device__ __forceinline__ void operator()() const {} };
+// `on_wait` runs (all 32 lanes, converged) every time a poll came back without what the look-back needs
+template <class A, int OP, class F = SpNoHook>
 __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, int t, int lane, unsigned long long m, unsigned long long xb,
-                                                unsigned sleep_ns = 0, bool gpu_scope = false) {
+                                                unsigned sleep_ns = 0, bool gpu_scope = false, F on_wait = F()) {
   A acc = A(0); bool have = false;
   int look = t - 1 - lane;
   for (;;) {
@@ -978,6 +980,7 @@ __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, 
       first = tb ? __ffs((int)tb) - 1 : 32;
       const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
       if ((pb & need) == need) break;
+      on_wait();
       if (sleep_ns) __nanosleep(sleep_ns);
       if (!pub && lane <= first) { if (gpu_scope) desc_load_gpu(desc + 2 * (long long)look, m, xb); else desc_load(desc + 2 * (long long)look, m, xb); }
     }
@@ -1017,6 +1020,11 @@ __device__ __forceinline__ A chain_lookback_pre(const unsigned long long* desc, 
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_THREADS = SG_THREADS + 32;
 constexpr int WS_SMEM = 115712;                                   // two CTAs per SM: (228 KB - 2 * 1 KB reserved) / 2; 496 B of small state + alignment + 7 tile buffers
+__device__ __forceinline__ bool sp_mbar_test(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
 __device__ __forceinline__ void sp_mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
 // LB: bytes per label (8: int64, 4: int32 -- rows of 32 bytes with the 32-byte swizzle: unit k of row t sits at k ^ ((t >> 2) & 1))
@@ -1071,12 +1079,14 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams 
 
   if (wrp == SG_THREADS / 32) {
     // ---------------- the ninth warp: block-level scan, descriptors, look-back, loads ----------------
-    for (int it = 0;; ++it) {
-      const int tile = it * grid + cta;
-      if (tile >= nfull) break;
-      const int s = it % SP_STAGES, slot = it & 1;
-      unsigned long long lm = 2ull, lxb = 0ull;
-      sp_mbar_wait(bar_agg + 8 * slot, (unsigned)(it >> 1) & 1u);
+    // Publishing a tile's aggregate must not wait for the look-back of the tile before it: the neighbour's look-back waits
+    // for exactly that aggregate, and a serial "look back, then publish the next" turned every missed poll into a delay
+    // handed down the grid (4 polls per tile, 2.5 us per iteration).  So while a look-back polls, the warp keeps checking
+    // whether the data warps have delivered the NEXT tile and publishes it at once (one tile ahead at most: the data
+    // warps wait for the prefix of tile i - 1 before they start tile i + 1).
+    struct Pub { bool fe, agg_f; A xe, agg_x; unsigned long long lm, lxb; };
+    auto publish = [&](int it, Pub& P) {                                 // the 8 warps of iteration `it` have arrived
+      const int tile = it * grid + cta, s = it % SP_STAGES, slot = it & 1;
       bool f = true; A x = A(0);
       if (lane < SG_THREADS / 32) { f = s_aggf[slot * 8 + lane] != 0u; x = scan_unbits<A>(s_aggx[slot * 8 + lane]); }
       bool fi = f; A xi = x;                                             // inclusive over warps 0 .. lane
@@ -1086,29 +1096,48 @@ __global__ void __launch_bounds__(WS_THREADS, 2) k_seg_scan_ws(const ScanParams 
         const A xt = __shfl_up_sync(0xffffffffu, xi, o);
         if (lane >= o) { if (!fi) xi = ScanOp<A, OP>::apply(xt, xi); fi = fi | ft; }
       }
-      const bool fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); const A xe = __shfl_up_sync(0xffffffffu, xi, 1);
-      const bool agg_f = __shfl_sync(0xffffffffu, (int)fi, SG_THREADS / 32 - 1); const A agg_x = __shfl_sync(0xffffffffu, xi, SG_THREADS / 32 - 1);
+      P.fe = __shfl_up_sync(0xffffffffu, (int)fi, 1); P.xe = __shfl_up_sync(0xffffffffu, xi, 1);
+      P.agg_f = __shfl_sync(0xffffffffu, (int)fi, SG_THREADS / 32 - 1); P.agg_x = __shfl_sync(0xffffffffu, xi, SG_THREADS / 32 - 1);
       if (lane == 0) {
-        if (gpu_scope) desc_store_gpu(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
-        else desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (agg_f ? 0x100ull : 0ull), scan_bits<A>(agg_x));
+        if (gpu_scope) desc_store_gpu(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (P.agg_f ? 0x100ull : 0ull), scan_bits<A>(P.agg_x));
+        else desc_store(desc + 2 * (long long)tile, (tile == 0 ? 2ull : 1ull) | (P.agg_f ? 0x100ull : 0ull), scan_bits<A>(P.agg_x));
       }
-      if (tile - 1 - lane >= 0) { if (gpu_scope) desc_load_gpu(desc + 2 * (long long)(tile - 1 - lane), lm, lxb); else desc_load(desc + 2 * (long long)(tile - 1 - lane), lm, lxb); }
+      P.lm = 2ull; P.lxb = 0ull;
+      if (tile - 1 - lane >= 0) { if (gpu_scope) desc_load_gpu(desc + 2 * (long long)(tile - 1 - lane), P.lm, P.lxb); else desc_load(desc + 2 * (long long)(tile - 1 - lane), P.lm, P.lxb); }
       if (lane == 0) {
         const int next = (it + SP_STAGES) * grid + cta;                  // every reader of stage s has arrived
         if (next < nfull) issue(s, next);
       }
+    };
+    Pub cur, nxt;
+    bool have_nxt = false;
+    for (int it = 0;; ++it) {
+      const int tile = it * grid + cta;
+      if (tile >= nfull) break;
+      const int slot = it & 1;
+      if (have_nxt) { cur = nxt; have_nxt = false; }
+      else { sp_mbar_wait(bar_agg + 8 * slot, (unsigned)(it >> 1) & 1u); publish(it, cur); }
       A c = A(0);
       const bool have_c = tile > 0;
       if (have_c) {
-        c = chain_lookback_pre<A, OP>(desc, tile, lane, lm, lxb, sleep_ns, gpu_scope);
+        auto ahead = [&]() {
+          const int nit = it + 1;
+          if (have_nxt || nit * grid + cta >= nfull) return;
+          const bool ok = sp_mbar_test(bar_agg + 8 * (nit & 1), (unsigned)(nit >> 1) & 1u);
+          if (__shfl_sync(0xffffffffu, (int)ok, 0)) {
+            if (!ok) sp_mbar_wait(bar_agg + 8 * (nit & 1), (unsigned)(nit >> 1) & 1u);   // (lane 0 saw it complete: immediate)
+            publish(nit, nxt); have_nxt = true;
+          }
+        };
+        c = chain_lookback_pre<A, OP>(desc, tile, lane, cur.lm, cur.lxb, sleep_ns, gpu_scope, ahead);
         if (lane == 0) {
-          const unsigned long long incl = scan_bits<A>(agg_f ? agg_x : ScanOp<A, OP>::apply(c, agg_x));
+          const unsigned long long incl = scan_bits<A>(cur.agg_f ? cur.agg_x : ScanOp<A, OP>::apply(c, cur.agg_x));
           if (gpu_scope) desc_store_gpu(desc + 2 * (long long)tile, 2ull | 0x100ull, incl); else desc_store(desc + 2 * (long long)tile, 2ull | 0x100ull, incl);
         }
       }
       if (lane < SG_THREADS / 32) {                                      // warp `lane`: exclusive prefix inside the tile, carry included
         bool have = false; A e = A(0);
-        if (lane > 0) { e = xe; have = true; if (have_c && !fe) e = ScanOp<A, OP>::apply(c, xe); }
+        if (lane > 0) { e = cur.xe; have = true; if (have_c && !cur.fe) e = ScanOp<A, OP>::apply(c, cur.xe); }
         else if (have_c) { e = c; have = true; }
         s_prex[slot * 8 + lane] = scan_bits<A>(e);
         s_preh[slot * 8 + lane] = have ? 1u : 0u;
