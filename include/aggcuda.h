@@ -190,8 +190,9 @@ int         agc_apply_carry(int32_t op, const void* labels, int32_t label_dtype,
 /* deterministic fixed-order mode: instead of agc_aggregate(req | AGC_F_ACC_ONLY), fill the accumulator tables of a floating
  * sum / sumofsquares / mean / var(std) / prod by walking every group's elements in their original order (`order`, `offsets`
  * from agc_group_order): one warp per group, lane-strided sequential f64 additions, fixed butterfly across the lanes.  The
- * result's bits depend on the input alone.  With AGC_F_PASS2 only the second pass of var / std runs (T0 holds the merged
- * means).  Finalise with agc_aggregate(req | AGC_F_FIN_ONLY). */
+ * result's bits depend on the input alone.  With AGC_F_PASS2 only the second pass of var / std runs (T0 / T1 hold the sums and
+ * counts merged over the shards; T2 receives this shard's squared deviations from the global mean).  Finalise with
+ * agc_aggregate(req | AGC_F_FIN_ONLY). */
 int         agc_ordered_accumulate(const agc_request_t* req, const int64_t* order, const int64_t* offsets, void* stream);
 
 /* first / last over shards (after the index tables were merged and req was finalised with AGC_F_FIN_ONLY): pack writes

@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(256) k_ordered_accumulate(const OrderedParams 
       for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       if (lane == 0) { p.t.t0f[g] = acc; p.t.t1[g] = cnt; p.t.b1[g] = cnt > 0; }
     } else {
-      acc = p.t.t0f[g]; cnt = p.t.t1[g];                      // merged over the ranks by the caller
+      acc = p.t.t0f[g]; cnt = p.t.t1[g];                      // the sums and counts of ALL ranks (merged in rank order by the caller)
     }
     if (p.op == AGC_OP_VAR) {
-      const double mean = pass2_only ? acc : acc / (double)cnt;   // pass2_only: T0 already holds the mean (k_means_inplace)
+      const double mean = acc / (double)cnt;
       double m2 = 0.0;
       for (long long k = lo + lane; k < hi; k += 32) {
         const double v = ord_load(p.a, p.a_dtype, p.order[k]);

@@ -200,18 +200,23 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
         if ordered:
             # fixed-order mode: every rank adds its own elements in element order, the per-rank tables are folded in RANK order
             # (all-gather + agc_rank_fold) instead of an all-reduce whose association order is the library's business
-            if c.base in ("var", "std"):
-                raise NotImplementedError("deterministic var / std over shards is not built (single GPU: deterministic=True works)")
             order_t, offsets_t = ac._group_order(c)
             req.flags = base_flags | _abi.F_ACC_ONLY
             if lib.agc_ordered_accumulate(C.byref(req), order_t.data_ptr(), offsets_t.data_ptr(), stream):
                 raise RuntimeError(_abi.last_error())
             _merge_in_rank_order(lib, req, ws, group, device, stream)
+            if c.base in ("var", "std"):
+                # second pass against the GLOBAL mean (sums and counts of all ranks are in T0 / T1 now): every rank's squared
+                # deviations in element order, then the T2 tables folded in rank order as well
+                req.flags = base_flags | _abi.F_ACC_ONLY | _abi.F_PASS2
+                if lib.agc_ordered_accumulate(C.byref(req), order_t.data_ptr(), offsets_t.data_ptr(), stream):
+                    raise RuntimeError(_abi.last_error())
+                _merge_in_rank_order(lib, req, ws, group, device, stream, second_pass=True)
         else:
             run(base_flags | _abi.F_ACC_ONLY)
             req.flags = base_flags
             _merge_packed(lib, req, ws, status, group, device, stream)
-        if c.base in ("var", "std", "argmax", "argmin"):
+        if c.base in ("var", "std", "argmax", "argmin") and not ordered:
             run(base_flags | _abi.F_ACC_ONLY | _abi.F_PASS2 | _abi.F_NO_INIT)
             req.flags = base_flags | _abi.F_PASS2
             _merge_packed(lib, req, ws, status, group, device, stream)
@@ -233,9 +238,10 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
     return ac._finish_shape_torch(c, ac._as_user_tensor(out))
 
 
-def _merge_in_rank_order(lib, req, ws, group, device, stream):
-    """Deterministic merge of the (sum | product, count, touched) tables: all-gather, then fold rank 0, 1, 2, ... in that
-    order on every rank (agc_rank_fold with rank = world) -- the association order of the floating additions is fixed."""
+def _merge_in_rank_order(lib, req, ws, group, device, stream, second_pass=False):
+    """Deterministic merge of the (sum | product, count, touched) tables -- or, after the second pass of var / std, of the
+    squared-deviation table T2: all-gather, then fold rank 0, 1, 2, ... in that order on every rank (agc_rank_fold with
+    rank = world) -- the association order of the floating additions is fixed."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -245,6 +251,13 @@ def _merge_in_rank_order(lib, req, ws, group, device, stream):
     t1 = ws[s8:s8 + size * 8].view(torch.int64)
     b1 = ws[3 * s8 + (size + 255) // 256 * 256:3 * s8 + (size + 255) // 256 * 256 + size]
     red = 3 if req.op == _abi.OP["prod"] else 0
+    if second_pass:
+        t2 = ws[2 * s8:2 * s8 + size * 8].view(torch.float64)
+        gathered = torch.empty((world, size), dtype=t2.dtype, device=device)
+        dist.all_gather_into_tensor(gathered, t2, group=group)
+        if lib.agc_rank_fold(gathered.data_ptr(), world, size, _abi.DT["float64"], 0, t2.data_ptr(), stream):
+            raise RuntimeError(_abi.last_error())
+        return
     for tab, code, rcode in ((t0, _abi.DT["float64"], red), (t1, _abi.DT["int64"], 0)):
         gathered = torch.empty((world, size), dtype=tab.dtype, device=device)
         dist.all_gather_into_tensor(gathered, tab, group=group)

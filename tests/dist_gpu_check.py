@@ -47,6 +47,16 @@ def main():
         else:
             np.testing.assert_array_equal(part, full, err_msg=func)
         checked += 1
+    # ---- deterministic fixed-order mode over shards: per-rank tables from the fixed-order kernel, folded in rank order (var / std:
+    #      second pass against the global mean).  Same bits on every run, and the single-GPU result within f64 rounding ----------
+    a64c = np.random.default_rng(11).standard_normal(n) + 3.0          # (a64 carries NaNs: only the nan-function sees numbers there)
+    for func, arr, kw in (("sum", a64c, {}), ("mean", a64c, {}), ("var", a64c, dict(ddof=1)), ("std", a64c, {}), ("nanvar", a64, {}), ("var", a32, {})):
+        full = aggregate(torch.from_numpy(gidx).cuda(), torch.from_numpy(arr).cuda(), func=func, size=groups, deterministic=True, **kw).cpu().numpy()
+        parts = [aggregate_sharded(torch.from_numpy(gidx[lo:hi]).cuda(), torch.from_numpy(arr[lo:hi]).cuda(), func=func, size=groups,
+                                   deterministic=True, **kw).cpu().numpy() for _ in range(2)]
+        assert parts[0].tobytes() == parts[1].tobytes(), f"deterministic {func}: two runs differ"
+        np.testing.assert_allclose(parts[0], full, rtol=1e-11 if arr.dtype == np.float64 else 1e-5, equal_nan=True, err_msg=f"deterministic {func}")
+        checked += 1
     # tables larger than one SM's shared memory: one-word sums, split mean, hot-key cache, run kernel under ACC_ONLY
     groups2 = 120000
     for dist_name in ("uniform", "sorted", "zipf"):
