@@ -162,7 +162,12 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
         raise NotImplementedError("aggregate_sharded: sort needs whole groups on one device (replicas only)")
     plan = c.plan
     if plan.form == "axis":
-        return _sharded_axis(c, group_idx, a, func, size, fill_value, order, dtype, axis, group, kwargs)
+        if plan.axis == len(plan.dims) - 1 and len(plan.dims) >= 2:
+            return _sharded_axis(c, group_idx, a, func, size, fill_value, order, dtype, axis, group, kwargs)
+        # any other axis: the shards are slices ALONG the labelled axis (group_idx is the matching slice), every rank holds
+        # partial tables for the whole output and they merge like Form 1's
+        if c.base in ac._N_TO_N or c.base in ("first", "last", "argmax", "argmin"):
+            raise NotImplementedError("aggregate_sharded, Form 3 along the labelled axis: reductions without element positions only")
     if c.base in ac._N_TO_N:
         if plan.form != "flat":
             raise ValueError(f"cannot reshape array of size {plan.n} into shape {tuple(plan.out_shape)}")

@@ -118,6 +118,16 @@ def main():
             assert part.shape == full.shape
             np.testing.assert_allclose(part, full, rtol=1e-5, err_msg=f"form3 {func}")
         checked += 1
+    # Form 3 on another axis: shards are slices along the LABELLED axis, the partial tables merge like Form 1's
+    a3t = rng.random((3000, 96)).astype(np.float32)
+    b3 = np.linspace(0, 3000, world + 1).astype(int)
+    q0, q1 = b3[rank], b3[rank + 1]
+    for func in ("sum", "mean", "max", "var"):
+        full = aggregate(torch.from_numpy(g3).cuda(), torch.from_numpy(a3t).cuda(), func=func, size=40, axis=0).cpu().numpy()
+        part = aggregate_sharded(torch.from_numpy(g3[q0:q1]).cuda(), torch.from_numpy(a3t[q0:q1]).cuda(), func=func, size=40, axis=0).cpu().numpy()
+        assert part.shape == full.shape == (40, 96), (func, part.shape, full.shape)
+        np.testing.assert_allclose(part, full, rtol=1e-5, atol=1e-6, err_msg=f"form3 axis=0 {func}")
+        checked += 1
     dist.barrier()
     if rank == 0:
         print(f"dist_gpu_check ok: {checked} functions, world={world}")
