@@ -13,7 +13,10 @@ sum of squared deviations; extreme key -> first matching index).
 What shards, and how:
   * Form 1 / 2 (flat labels) and Form 4 / 5 (``group_idx`` of shape (ndim, n)): slices along N, merge as above;
   * Form 3 on the LAST axis: slices along the outer dimension -- the outputs are disjoint, the only collective is the
-    all-gather that hands every rank the full result;
+    all-gather that hands every rank the full result; Form 3 on any other axis: slices along the labelled axis, partial
+    tables for the whole output, merge as above;
+  * ``deterministic=True``: the per-rank tables come from the fixed-order kernel and are all-gathered and folded in RANK
+    order instead of all-reduced (var / std: also their second pass, against the global mean);
   * N -> N functions (cumsum / cumprod / cummax / cummin and nan-forms): local scan + cross-GPU carry exchange: the
     per-group totals of every rank are all-gathered, rank r folds the totals of the ranks before it (``agc_rank_fold``)
     and adds that carry to its local scan (``agc_apply_carry``); every rank returns ITS shard of the result;
@@ -336,7 +339,8 @@ def _sharded_scan(c, group, check):
 
 def _sharded_axis(c, group_idx, a, func, size, fill_value, order, dtype, axis, group, kwargs):
     """Form 3.  Last axis: every rank holds a slice of the OUTER dimension, its rows are nobody else's -- local aggregate,
-    then one all-gather so that every rank has the full result.  Other axes would slice the reduced axis; not built."""
+    then one all-gather so that every rank has the full result.  (Any other axis: aggregate_sharded merges partial tables, shards
+    being slices along the labelled axis.)"""
     import torch
     import torch.distributed as dist
     plan = c.plan
