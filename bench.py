@@ -588,6 +588,25 @@ def main():
                                       "frac_of_peak": round((n * 12 + g_ * 4) / ms * 1e-6 / peak, 4)})
                     except Exception as e:            # noqa: BLE001
                         sweep.append({"func": f_, "groups": g_, "dist": dname, "error": str(e)[:120]})
+                # the int32-label variant SURVEY 8(d) asks for (8 instead of 12 B/element), at the headline group count
+                if g_ == 100000 and dname == "uniform" and world == 1:
+                    lab32 = lab2.to(torch.int32)
+                    for f_ in ("sum", "max"):
+                        try:
+                            for _ in range(2):
+                                step(lab32, a, f_, g_)
+                            barrier()
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
+                            for _ in range(3):
+                                step(lab32, a, f_, g_)
+                            e1.record(); barrier()
+                            ms = e0.elapsed_time(e1) / 3
+                            sweep.append({"func": f_, "groups": g_, "dist": dname, "labels": "int32", "ms": round(ms, 4), "gelem_s": round(n / ms * 1e-6, 2),
+                                          "frac_of_peak": round((n * 8 + g_ * 4) / ms * 1e-6 / peak, 4)})
+                        except Exception as e:        # noqa: BLE001
+                            sweep.append({"func": f_, "groups": g_, "dist": dname, "labels": "int32", "error": str(e)[:120]})
+                    del lab32
                 del lab2
 
     if rank != 0:
