@@ -22,3 +22,25 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["vs_baseline"] is None
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--log2n", "24", "--steps", "4", "--warmup", "3", "--no-sweep",
+                          "--cpu-log2n", "18"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "verified"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 4 and line["unit"] == "Gelem/s" and line["value"] > 0
+    rf = line["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["kernel_ms"] > 0 and rf["kernel_ms"] <= line["ms_per_step"] * 1.05
+    assert line["gpu_launches"] > 0
+    assert line["verified"]["ok"] is True
+    assert line["e2e"]["h2d_bytes_per_step"] == (1 << 24) * 12 and line["e2e"]["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] > 0
