@@ -279,6 +279,17 @@ __global__ void k_group_keys(Indexer ix, long long n, unsigned* keys, unsigned* 
   if (bad) status[AGC_ST_BADLABEL] = 1;
   if (uns) *unsorted = 1;
 }
+// random gathers of single elements: ask L2 for the smallest DRAM fetch (64 bytes) instead of its default
+__device__ __forceinline__ unsigned long long gather64(const void* base, unsigned long long idx) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(v) : "l"((const unsigned long long*)base + idx));
+  return v;
+}
+__device__ __forceinline__ unsigned gather32(const void* base, unsigned long long idx) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b32 %0, [%1];" : "=r"(v) : "l"((const unsigned*)base + idx));
+  return v;
+}
 __global__ void k_zero_int(int* p) { p[0] = 0; p[1] = 0; }
 // 4096 neighbouring pairs spread over the labels: random labels show an inversion here with certainty, and the persistent
 // direct scan (which finishes its pass once started) then never starts
@@ -333,12 +344,13 @@ __device__ __forceinline__ A scan_input(const ScanParams& p, unsigned src_pos, b
     if (std::is_same<A, double>::value) {
       double v;
       if (p.a_dtype == AGC_DT_F32) v = ((const float*)p.a)[src_pos];
-      else if (p.a_dtype == AGC_DT_F64) v = ((const double*)p.a)[src_pos];
-      else if (p.a_u64) v = (double)((const unsigned long long*)p.a)[src_pos];
+      else if (p.a_dtype == AGC_DT_F64) v = __longlong_as_double((long long)gather64(p.a, src_pos));
+      else if (p.a_u64) v = (double)gather64(p.a, src_pos);
       else v = (double)load_int(p.a, p.a_dtype, src_pos);
       if (nanskip && v != v) v = OP == SC_SUM ? 0.0 : 1.0;
       return (A)v;
     } else {
+      if (p.a_dtype == AGC_DT_I64 || p.a_dtype == AGC_DT_U64) return (A)(long long)gather64(p.a, src_pos);
       return (A)load_int(p.a, p.a_dtype, src_pos);
     }
   } else {
@@ -349,7 +361,7 @@ __device__ __forceinline__ A scan_input(const ScanParams& p, unsigned src_pos, b
       if (v != v) return (A)((nanskip || !head) ? ident : absorb);   // numba: a NaN only sticks when it opens the group
       return (A)key_of(v);
     }
-    long long v = load_int(p.a, p.a_dtype, src_pos);
+    long long v = (p.a_dtype == AGC_DT_I64 || p.a_dtype == AGC_DT_U64) ? (long long)gather64(p.a, src_pos) : load_int(p.a, p.a_dtype, src_pos);
     return (A)(p.a_u64 ? key_of((unsigned long long)v) : v);
   }
 }
@@ -1388,8 +1400,8 @@ __global__ void k_gather_by_pos(const void* a, int eb, long long n, const unsign
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
     const unsigned s = src_pos[i];
-    if (eb == 8) ((unsigned long long*)staged)[i] = ((const unsigned long long*)a)[s];
-    else ((unsigned*)staged)[i] = ((const unsigned*)a)[s];
+    if (eb == 8) ((unsigned long long*)staged)[i] = gather64(a, s);
+    else ((unsigned*)staged)[i] = gather32(a, s);
   }
 }
 __global__ void k_order_widen(const unsigned* p0, const unsigned* p1, const int* unsorted, long long n, long long* order) {
