@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AGC_ABI_VERSION 4
+#define AGC_ABI_VERSION 5
 
 /* element dtypes (values, labels and outputs) */
 enum {
@@ -199,6 +199,11 @@ int         agc_ordered_accumulate(const agc_request_t* req, const int64_t* orde
  * carrier[g] = bits of out[g] where THIS shard holds the group's winning element, else 0 (one int64 SUM all-reduce hands
  * every rank the owner's bits); unpack stores them into out[g] for every non-empty group. */
 int         agc_owner_pack(const agc_request_t* req, int64_t* carrier, int32_t unpack, void* stream);
+
+/* float16 values / results (check_dtype keeps float16 for float16 input, utils.py:435-470; the kernels compute them as
+ * float32): n elements float16 -> float32 (to_half == 0, exact) or float32 -> float16 (round to nearest even, as
+ * numpy's astype), device pointers, src != dst. */
+int         agc_convert_f16(const void* src, void* dst, int64_t n, int32_t to_half, void* stream);
 
 /* Host side of the H2D path for numpy labels (the reference hands `group_idx` to its kernels as it is,
  * aggregate_numpy.py:370-392; here the labels have to cross PCIe first, and for int64 labels that is 8 of the 12 bytes

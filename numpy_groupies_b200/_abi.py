@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaggcuda.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_NDIM = 8
 
 # ---- enums (mirror include/aggcuda.h) ----------------------------------------------------------
@@ -56,7 +56,7 @@ EXPORTS = ("agc_abi_version", "agc_last_error", "agc_workspace_bytes", "agc_part
            "agc_profile_enable", "agc_profile_last_ms", "agc_profile_ms", "agc_launch_count", "agc_tuning",
            "agc_label_scan_workspace_bytes", "agc_label_scan", "agc_mark_present", "agc_multi_arange",
            "agc_pack_tables", "agc_rank_fold", "agc_apply_carry", "agc_owner_pack", "agc_ordered_accumulate",
-           "agc_host_narrow_labels", "agc_host_copy_stream")
+           "agc_host_narrow_labels", "agc_host_copy_stream", "agc_convert_f16")
 
 _lib = None
 
@@ -116,6 +116,8 @@ def load():
     lib.agc_host_narrow_labels.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
     lib.agc_host_copy_stream.restype = C.c_int
     lib.agc_host_copy_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.agc_convert_f16.restype = C.c_int
+    lib.agc_convert_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.agc_profile_enable.restype = C.c_int
     lib.agc_profile_enable.argtypes = [C.c_int]
     lib.agc_profile_last_ms.restype = C.c_float

@@ -181,8 +181,10 @@ def _tensor_np_dtype(t):
 _STAGE = {"bufs": None, "pool": None, "events": None}
 _STAGE_CHUNK = 32 << 20          # bytes per pinned staging buffer
 _STAGE_BUFS = 3
-# host threads that fill the staging buffers (memcpy / label narrowing release the GIL): half the cores, at most 8
-_STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(2, min(8, (os.cpu_count() or 4) // 2))
+# host threads that fill the staging buffers (memcpy / label narrowing release the GIL): all cores but two, at most 14
+# (measured on the 16-core B200 host, N = 2^28, pageable int64 labels + f32 values: 8 threads 72-77 ms, 12 threads 70-71,
+#  14 threads 67-69 -- profiles/r02j_stage_threads.jsonl; two cores stay free for the caller and the driver's copy thread)
+_STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(2, min(14, (os.cpu_count() or 4) - 2))
 _NARROW_LABELS = os.environ.get("AGC_NARROW_LABELS", "1") != "0"
 _NARROW_PINNED = os.environ.get("AGC_NARROW_PINNED", "0") != "0"      # page-locked labels too (measured slower than their plain DMA)
 # arrays of at least this many bytes go through the staging ring / as one asynchronous DMA; smaller ones as a plain copy
@@ -301,6 +303,21 @@ def _from_tensor(t):
 def _empty(n, dtype, device):
     torch = _t()
     return _Dev(torch.empty(int(n), dtype=getattr(torch, _CARRIER[_dtname(dtype)]), device=device), dtype)
+
+
+def _convert_f16(dev, to_half):
+    """float16 <-> float32 on the device with the library's own kernel (agc_convert_f16): float16 values are computed as
+    float32 and float16 results are rounded back once, at the end (check_dtype keeps float16 for float16 input,
+    utils.py:435-470).  torch only allocates the destination."""
+    torch = _t()
+    src = dev.t.contiguous()
+    dst = torch.empty(src.shape, dtype=torch.float16 if to_half else torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = _abi.load().agc_convert_f16(src.data_ptr() if src.numel() else 0, dst.data_ptr() if dst.numel() else 0,
+                                         src.numel(), 1 if to_half else 0, _stream_ptr(src.device))
+    if rc:
+        raise RuntimeError(f"agc_convert_f16 failed ({rc}): {_abi.last_error()}")
+    return _Dev(dst, np.float16 if to_half else np.float32)
 
 
 def _download(dev, shape=None):
@@ -597,7 +614,7 @@ def _values_on_device(c, device):
     if _is_tensor(a):
         dev = _from_tensor(a)
         if _dtname(dev.dtype) in _COMPUTE_AS:
-            dev = _Dev(dev.t.to(_t().float32), np.float32)
+            dev = _convert_f16(dev, False)
         dev.t = dev.t.reshape(-1)
         return dev
     arr = np.ascontiguousarray(a)
@@ -675,7 +692,7 @@ def _run_device(c):
             _LAST["regime"] = c.regime
             _LAST["probe"] = tuple(int(v) for v in st[4:7])
     if out_np_dtype != compute_out:                         # float16 results
-        out = _Dev(out.t.to(getattr(torch, out_np_dtype.name)), out_np_dtype)
+        out = _convert_f16(out, True)
     return out
 
 
@@ -979,7 +996,7 @@ def _fused_family(group_idx, a, members, family, size, fill_value, order, axis, 
                 flags |= _abi.F_KEYS_IN_T2
             call(c.base, flags, c, o)
             if c.out_dtype != compute_out:
-                o = _Dev(o.t.to(getattr(torch, c.out_dtype.name)), c.out_dtype)
+                o = _convert_f16(o, True)
             return o
 
         first = [nm for nm in members if bases[nm] not in ("var", "std")]

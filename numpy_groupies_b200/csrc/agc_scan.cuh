@@ -7,6 +7,7 @@
 // Sortedness of the flat labels is detected on the device; already-sorted labels skip every sort
 // pass without a host round trip (the sort kernels read the flag and return).
 #pragma once
+#include <cuda_fp16.h>
 #include "agc_generic.cuh"
 
 namespace agc {
@@ -46,6 +47,36 @@ __global__ void k_unpack(const void* table, int eb, long long size, const void* 
     }
   }
   if (bad) status[AGC_ST_BADLABEL] = 1;
+}
+
+// float16 <-> float32 (the kernels compute float16 data as float32: exact on the way in, round-to-nearest-even on the
+// way out, the same as numpy's astype -- check_dtype hands float16 results back as float16, utils.py:435-470).
+// 8 elements per thread-iteration: one 128-bit access on the half side, two on the float side.
+template <bool TO_HALF>
+__global__ void k_convert_f16(const void* __restrict__ src, void* __restrict__ dst, long long n) {
+  const long long nvec = n >> 3, stride = (long long)gridDim.x * blockDim.x;
+  const bool vec_ok = (((unsigned long long)src | (unsigned long long)dst) & 15ull) == 0;
+  long long done = 0;
+  if (vec_ok) {
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+      if (TO_HALF) {
+        const float4 a = ((const float4*)src)[2 * v], b = ((const float4*)src)[2 * v + 1];
+        __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+        ((int4*)dst)[v] = *(const int4*)h;
+      } else {
+        const int4 raw = ((const int4*)src)[v];
+        const __half2* h = (const __half2*)&raw;
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+        ((float4*)dst)[2 * v] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        ((float4*)dst)[2 * v + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+      }
+    }
+    done = nvec << 3;
+  }
+  for (long long i = done + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (TO_HALF) ((__half*)dst)[i] = __float2half_rn(((const float*)src)[i]);
+    else ((float*)dst)[i] = __half2float(((const __half*)src)[i]);
+  }
 }
 
 static thread_local const char* g_scan_err = "";

@@ -315,6 +315,17 @@ int agc_unpack(const void* table, int32_t elem_bytes, int64_t size, const void* 
   return 0;
 }
 
+int agc_convert_f16(const void* src, void* dst, int64_t n, int32_t to_half, void* stream) {
+  if (n < 0) return fail(-3, "agc_convert_f16: negative length");
+  if (n == 0) return 0;
+  if (!src || !dst) return fail(-6, "agc_convert_f16: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (to_half) AGC_COUNT_LAUNCH(1), agc::k_convert_f16<true><<<grid_for((n + 7) >> 3, 256, 8), 256, 0, st>>>(src, dst, n);
+  else AGC_COUNT_LAUNCH(1), agc::k_convert_f16<false><<<grid_for((n + 7) >> 3, 256, 8), 256, 0, st>>>(src, dst, n);
+  AGC_CUDA_OK("convert_f16");
+  return 0;
+}
+
 int agc_pack_tables(const agc_pack_seg_t* segs, int32_t nseg, void* packed, int32_t carrier_dtype, int32_t unpack, void* stream) {
   if (nseg < 1 || nseg > agc::PK_MAX_SEGS || !segs || !packed) return fail(-6, "agc_pack_tables: bad segment list");
   if (carrier_dtype != AGC_DT_F64 && carrier_dtype != AGC_DT_I64) return fail(-3, "agc_pack_tables: the carrier is float64 or int64");

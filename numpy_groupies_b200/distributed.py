@@ -242,7 +242,7 @@ def aggregate_sharded(group_idx, a, func="sum", size=None, fill_value=0, order="
             ac._mark_validated(c)
             ac._LAST["regime"] = int(st[_abi.ST_REGIME])
     if c.out_dtype != compute_out:
-        out = ac._Dev(out.t.to(getattr(torch, c.out_dtype.name)), c.out_dtype)
+        out = ac._convert_f16(out, True)
     return ac._finish_shape_torch(c, ac._as_user_tensor(out))
 
 

@@ -373,3 +373,49 @@ def test_validated_labels_are_remembered_until_they_change():
     assert aggregate(g2, a, func="sum", size=groups, check=False).shape == (groups,)    # never checked, never remembered
     with pytest.raises(ValueError):
         aggregate(g2, a, func="sum", size=groups)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 4099, (1 << 20) + 5])
+@pytest.mark.parametrize("shift", [0, 1])
+def test_convert_f16_is_numpy_astype(n, shift):
+    """agc_convert_f16 (the library's own float16 <-> float32 kernel, no torch arithmetic on the product path): every bit
+    pattern class -- normals, subnormals, +-0, +-inf, NaN, round-to-nearest-even ties, overflow to inf -- and pointers that
+    are / are not 16-byte aligned (a view that starts one element in)."""
+    import torch
+    rng = np.random.default_rng(n + shift)
+    h = rng.integers(0, 1 << 16, n + shift, dtype=np.uint16).view(np.float16)
+    th = torch.from_numpy(h.view(np.int16)).cuda().view(torch.float16)[shift:]
+    f = ac._convert_f16(ac._Dev(th, np.float16), False).t
+    assert f.dtype == torch.float32
+    np.testing.assert_array_equal(f.cpu().numpy().view(np.uint32), h[shift:].astype(np.float32).view(np.uint32))
+    # float32 -> float16: random bit patterns (mostly huge / tiny exponents), values around the float16 grid (ties) and the
+    # overflow threshold
+    x = rng.integers(0, 1 << 32, n + shift, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    if n:
+        k = (n + shift) // 2
+        grid = rng.integers(0, 0x7c00, k, dtype=np.uint16).view(np.float16).astype(np.float32)
+        x[:k] = np.nextafter(grid, np.float32(np.inf)) if shift else grid + np.float32(0.5) * np.spacing(grid.astype(np.float16)).astype(np.float32)
+        x[-1] = np.float32(65520.0)
+    tx = torch.from_numpy(x.view(np.int32)).cuda().view(torch.float32)[shift:]
+    hh = ac._convert_f16(ac._Dev(tx, np.float32), True).t
+    assert hh.dtype == torch.float16
+    with np.errstate(over="ignore"):
+        ref = x[shift:].astype(np.float16)
+    got = hh.cpu().numpy()
+    nan = np.isnan(ref)
+    np.testing.assert_array_equal(np.isnan(got), nan)
+    np.testing.assert_array_equal(got.view(np.uint16)[~nan], ref.view(np.uint16)[~nan])
+
+
+def test_float16_device_tensors_in_and_out():
+    """float16 CUDA tensors go through agc_convert_f16 on the way in and on the way out; same answer as the numpy call."""
+    import torch
+    rng = np.random.default_rng(16)
+    g = rng.integers(0, 50, 10_000)
+    a = rng.random(10_000).astype(np.float16)
+    for func in ("sum", "mean", "max", "cumsum"):
+        ref = aggregate(g, a, func=func, size=50)
+        got = aggregate(torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda(), func=func, size=50)
+        assert got.is_cuda and got.dtype == torch.float16 and ref.dtype == np.float16, (func, got.dtype, ref.dtype)
+        np.testing.assert_array_equal(got.cpu().numpy().view(np.uint16), ref.view(np.uint16))
+        np.testing.assert_allclose(ref.astype(np.float64), oracle.aggregate(g, a, func=func, size=50).astype(np.float64), rtol=2e-3, atol=1e-3)
