@@ -52,6 +52,11 @@ __global__ void k_unpack(const void* table, int eb, long long size, const void* 
 // float16 <-> float32 (the kernels compute float16 data as float32: exact on the way in, round-to-nearest-even on the
 // way out, the same as numpy's astype -- check_dtype hands float16 results back as float16, utils.py:435-470).
 // 8 elements per thread-iteration: one 128-bit access on the half side, two on the float side.
+__device__ __forceinline__ unsigned f16x2_bits(float lo, float hi) {
+  return (unsigned)__half_as_ushort(__float2half_rn(lo)) | ((unsigned)__half_as_ushort(__float2half_rn(hi)) << 16);
+}
+__device__ __forceinline__ float f16_lo(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float f16_hi(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 template <bool TO_HALF>
 __global__ void k_convert_f16(const void* __restrict__ src, void* __restrict__ dst, long long n) {
   const long long nvec = n >> 3, stride = (long long)gridDim.x * blockDim.x;
@@ -61,14 +66,13 @@ __global__ void k_convert_f16(const void* __restrict__ src, void* __restrict__ d
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += stride) {
       if (TO_HALF) {
         const float4 a = ((const float4*)src)[2 * v], b = ((const float4*)src)[2 * v + 1];
-        __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
-        ((int4*)dst)[v] = *(const int4*)h;
+        uint4 o;
+        o.x = f16x2_bits(a.x, a.y); o.y = f16x2_bits(a.z, a.w); o.z = f16x2_bits(b.x, b.y); o.w = f16x2_bits(b.z, b.w);
+        ((uint4*)dst)[v] = o;
       } else {
-        const int4 raw = ((const int4*)src)[v];
-        const __half2* h = (const __half2*)&raw;
-        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-        ((float4*)dst)[2 * v] = make_float4(f0.x, f0.y, f1.x, f1.y);
-        ((float4*)dst)[2 * v + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+        const uint4 raw = ((const uint4*)src)[v];
+        ((float4*)dst)[2 * v] = make_float4(f16_lo(raw.x), f16_hi(raw.x), f16_lo(raw.y), f16_hi(raw.y));
+        ((float4*)dst)[2 * v + 1] = make_float4(f16_lo(raw.z), f16_hi(raw.z), f16_lo(raw.w), f16_hi(raw.w));
       }
     }
     done = nvec << 3;
