@@ -421,4 +421,5 @@ def test_float16_device_tensors_in_and_out():
         got = aggregate(torch.from_numpy(g).cuda(), torch.from_numpy(a).cuda(), func=func, size=50)
         assert got.is_cuda and got.dtype == torch.float16 and ref.dtype == np.float16, (func, got.dtype, ref.dtype)
         np.testing.assert_array_equal(got.cpu().numpy().view(np.uint16), ref.view(np.uint16))
-        np.testing.assert_allclose(ref.astype(np.float64), oracle.aggregate(g, a, func=func, size=50).astype(np.float64), rtol=2e-3, atol=1e-3)
+        if func != "cumsum":        # (the reference's float16 cumsum is one global running sum in float16: no yardstick)
+            np.testing.assert_allclose(ref.astype(np.float64), oracle.aggregate(g, a, func=func, size=50).astype(np.float64), rtol=2e-3, atol=1e-3)
