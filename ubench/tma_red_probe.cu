@@ -68,6 +68,37 @@ __global__ void __launch_bounds__(1024, 1) k_tma_red(const long long* __restrict
   if (via_tma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// What one uncovered element of `mean` costs the receiving side: WIDE 0 = two scalar REDs (f64 sum + u64 count, what the fused
+// table format pays today), 1 = one scalar f32 RED, 2 = one red.global.add.v2.f32 {x, 1}, 4 = one red.global.add.v4.f32
+// {x, 1, 0, 0} (one 16-byte slot per group: is a vector RED one operation of the L2 atomic unit or four?)
+template <int WIDE>
+__global__ void __launch_bounds__(1024, 1) k_wide_red(const long long* __restrict__ idx, const float* __restrict__ a, long long n, void* tabv) {
+  const long long nvec = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const int4 l0 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v);
+    const int4 l1 = ldg_stream(reinterpret_cast<const int4*>(idx) + 2 * v + 1);
+    const int4 av = ldg_stream(reinterpret_cast<const int4*>(a) + v);
+    const int g4[4] = {l0.x, l0.z, l1.x, l1.z};
+    const int x4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long g = g4[j];
+      const float x = __int_as_float(x4[j]);
+      if (WIDE == 0) {
+        red_f64(reinterpret_cast<double*>(tabv) + 2 * g, (double)x);
+        asm volatile("red.global.add.u64 [%0], %1;" :: "l"(reinterpret_cast<unsigned long long*>(tabv) + 2 * g + 1), "l"(1ull) : "memory");
+      } else if (WIDE == 1) {
+        asm volatile("red.global.add.f32 [%0], %1;" :: "l"(reinterpret_cast<float*>(tabv) + g), "f"(x) : "memory");
+      } else if (WIDE == 2) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(reinterpret_cast<float*>(tabv) + 2 * g), "f"(x), "f"(1.0f) : "memory");
+      } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(reinterpret_cast<float*>(tabv) + 4 * g), "f"(x), "f"(1.0f), "f"(0.0f), "f"(0.0f) : "memory");
+      }
+    }
+  }
+}
+
 template <class L> static double time_ms(L launch, int warm = 1, int reps = 3) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int i = 0; i < warm; ++i) launch();
@@ -115,6 +146,21 @@ int main(int argc, char** argv) {
     fflush(stdout);                                                                                                   \
   }
   RUN(0, 4) RUN(1, 1) RUN(1, 2) RUN(1, 4) RUN(1, 8) RUN(2, 4) RUN(2, 8)
+  {
+    void* wide; CK(cudaMalloc(&wide, G * 16)); CK(cudaMemset(wide, 0, G * 16));
+    const char* names[4] = {"two scalar REDs (f64 sum + u64 count)", "one red.global.add.f32", "one red.global.add.v2.f32", "one red.global.add.v4.f32"};
+    for (int ctas : {111, 148}) {
+      double ms[4];
+      ms[0] = time_ms([&] { k_wide_red<0><<<ctas, 1024>>>(idx, a, N, wide); });
+      ms[1] = time_ms([&] { k_wide_red<1><<<ctas, 1024>>>(idx, a, N, wide); });
+      ms[2] = time_ms([&] { k_wide_red<2><<<ctas, 1024>>>(idx, a, N, wide); });
+      ms[3] = time_ms([&] { k_wide_red<4><<<ctas, 1024>>>(idx, a, N, wide); });
+      for (int i = 0; i < 4; ++i) {
+        printf("{\"mode\": \"%s\", \"ctas\": %d, \"N\": %lld, \"G\": %lld, \"ms\": %.3f, \"g_elements_s\": %.1f}\n", names[i], ctas, N, G, ms[i], N / ms[i] * 1e-6);
+      }
+      fflush(stdout);
+    }
+  }
   // who bounds the scattered RED: the SM that sends it or the L2 / fabric that executes it?  The same N elements from fewer CTAs
   // (one CTA per SM): a sender-side bound scales with the number of SMs, a receiver-side bound does not
   for (int ctas : {18, 37, 55, 74, 92, 111, 129, 148}) {
