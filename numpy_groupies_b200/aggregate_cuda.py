@@ -184,7 +184,9 @@ _STAGE_BUFS = 3
 # host threads that fill the staging buffers (memcpy / label narrowing release the GIL): all cores but two, at most 14
 # (measured on the 16-core B200 host, N = 2^28, pageable int64 labels + f32 values: 8 threads 72-77 ms, 12 threads 70-71,
 #  14 threads 67-69 -- profiles/r02j_stage_threads.jsonl; two cores stay free for the caller and the driver's copy thread)
-_STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(2, min(14, (os.cpu_count() or 4) - 2))
+# Under torchrun every rank of the node has its own pool: the cores are shared out (LOCAL_WORLD_SIZE).
+_STAGE_THREADS = int(os.environ.get("AGC_STAGE_THREADS", 0)) or max(
+    2, min(14, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)) - 2))
 _NARROW_LABELS = os.environ.get("AGC_NARROW_LABELS", "1") != "0"
 _NARROW_PINNED = os.environ.get("AGC_NARROW_PINNED", "0") != "0"      # page-locked labels too (measured slower than their plain DMA)
 # arrays of at least this many bytes go through the staging ring / as one asynchronous DMA; smaller ones as a plain copy
