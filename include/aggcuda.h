@@ -238,7 +238,8 @@ int64_t     agc_launch_count(void);
  *          reduce / scan-tiles / apply variant
  *   key 7  sums / means on tables larger than one SM: thread-block clusters of this many SMs (2 | 4) own the table together
  *          and exchange records over DSMEM (k_team); 0 = partial table + global RED (default: the exchange measured slower than the REDs it saves)
- *   key 8  k_team runs while at most this percentage of the groups stays without a slot (default 60) */
+ *   key 8  k_team runs while at most this percentage of the groups stays without a slot (default 60)
+ *   key 9  CTAs of the partial-table kernel (0 = one per SM, default): the L2 takes scattered REDs best from 111-129 senders */
 int         agc_tuning(int key, int value);
 
 #ifdef __cplusplus

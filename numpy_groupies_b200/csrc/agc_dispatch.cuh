@@ -119,9 +119,11 @@ __global__ void __launch_bounds__(1024) k_skew_probe(const void* labels, long lo
 //                         Default 0: measured on B200, a record that travels through the exchange costs ~9 issue clocks per
 //                         SM (compaction, st.async, receive loop) where a global RED costs ~2.6 (profiles/r02_team_*.jsonl)
 //   key 8  AGC_TEAM_MAXU  k_team runs while at most this percentage of the groups stays without a slot (default 60)
+//   key 9  AGC_PART_GRID  CTAs of the partial-table k_fast (0 = one per SM, default).  The receiving side of the scattered REDs
+//                         peaks with 111-129 senders (ubench/tma_red_probe.cu: 151 G RED/s against 141 from 148 SMs)
 enum { TUNE_LARGE = 0, TUNE_CACHE_CTAS = 1, TUNE_SUM1 = 2, TUNE_SMEM1 = 3, TUNE_SMEM2 = 4, TUNE_UNCOV = 5, TUNE_SCAN_CHAIN = 6, TUNE_TEAM = 7,
-       TUNE_TEAM_MAXU = 8, TUNE_COUNT = 9 };
-static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+       TUNE_TEAM_MAXU = 8, TUNE_PART_GRID = 9, TUNE_COUNT = 10 };
+static int g_tune[TUNE_COUNT] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 inline void tuning_defaults_once() {
   const char* e;
   e = getenv("AGC_LARGE");      g_tune[TUNE_LARGE] = e ? atoi(e) : 1;
@@ -135,6 +137,7 @@ inline void tuning_defaults_once() {
   e = getenv("AGC_TEAM");       g_tune[TUNE_TEAM] = e ? atoi(e) : 0;
   if (g_tune[TUNE_TEAM] != 0 && g_tune[TUNE_TEAM] != 2 && g_tune[TUNE_TEAM] != 4) g_tune[TUNE_TEAM] = 0;
   e = getenv("AGC_TEAM_MAXU");  g_tune[TUNE_TEAM_MAXU] = e ? atoi(e) : 60;
+  e = getenv("AGC_PART_GRID");  g_tune[TUNE_PART_GRID] = e ? atoi(e) : 0;
 }
 inline void tuning_defaults() { static std::once_flag once; std::call_once(once, tuning_defaults_once); }
 
@@ -365,8 +368,10 @@ inline int try_fast_path(const agc_request_t* r, const Tables& t, cudaStream_t s
                        r->size * 4 > (long long)(cap1 / 12) * 5;   // the fused table would cover < 80 % of the groups
     p.choose = probe ? choose : nullptr; p.want = 0;
     // one launch group of k_fast<M> with `w` words per group; `with_a`: the kernel reads the values
+    const int sms_all = sms;
     auto run_fast = [&](int m, int w, bool with_a, long long max_per_cta) {
       p.cov = (int)pick_cov((size_t)w * 4, 1);
+      const int sms = (p.cov < p.size && g_tune[TUNE_PART_GRID] > 0 && g_tune[TUNE_PART_GRID] < sms_all) ? g_tune[TUNE_PART_GRID] : sms_all;
       const long long per_launch = (long long)sms * max_per_cta;
       for (long long off = 0; off < r->n && rc >= 0; off += per_launch) {
         p.n = r->n - off < per_launch ? r->n - off : per_launch;
