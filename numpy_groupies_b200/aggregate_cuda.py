@@ -53,10 +53,11 @@ def last_regime():
     return _LAST["regime"]
 
 
-def tuning(large=-1, cache_ctas=-1, sum1=-1, smem1=-1, smem2=-1, uncov_pct=-1, scan_chain=-1, team=-1, team_maxu=-1):
+def tuning(large=-1, cache_ctas=-1, sum1=-1, smem1=-1, smem2=-1, uncov_pct=-1, scan_chain=-1, team=-1, team_maxu=-1, part_grid=-1):
     """Kernel-selection knobs of libaggcuda (agc_tuning, include/aggcuda.h): for tests and A/B measurements."""
     lib = _abi.load()
-    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1, smem1, smem2, uncov_pct, scan_chain, team, team_maxu)))
+    return tuple(lib.agc_tuning(k, int(v)) for k, v in enumerate((large, cache_ctas, sum1, smem1, smem2, uncov_pct, scan_chain, team, team_maxu,
+                                                                  part_grid)))
 
 
 def _t():

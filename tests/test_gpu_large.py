@@ -838,3 +838,30 @@ def test_team_kernel_is_exact_for_dyadic_data_and_counts_hot_groups():
                 np.testing.assert_array_equal(mean, (ref_sum / ref_cnt).astype(np.float32))
     finally:
         ac.tuning(team=0, team_maxu=60, large=1)
+
+
+@pytest.mark.parametrize("func", ["sum", "mean", "max", "len"])
+def test_partial_table_kernel_on_fewer_ctas(func):
+    """agc_tuning key 9: the partial-table kernel on any number of CTAs (grid-stride loops, one table flush per CTA) gives the
+    same result -- bit for bit on dyadic data, whose sums are exact whatever the order."""
+    from numpy_groupies_b200 import aggregate_cuda as ac
+    rng = np.random.default_rng(99)
+    n, groups = (1 << 22) + 13, 100_000
+    a = (rng.integers(0, 1 << 24, n) * 2.0 ** -24).astype(np.float32)
+    gidx = rng.integers(0, groups, n)
+    try:
+        ac.tuning(large=3)
+        ref = aggregate(gidx, a, func=func, size=groups)
+        regime = ac.last_regime()
+        for grid in (1, 37, 100, 1000):                    # (more CTAs than SMs are ignored: one per SM)
+            ac.tuning(part_grid=grid)
+            got = aggregate(gidx, a, func=func, size=groups)
+            assert ac.last_regime() == regime
+            np.testing.assert_array_equal(got, ref)
+    finally:
+        ac.tuning(large=1, part_grid=0)
+    want = oracle.aggregate(gidx, a, func=func, size=groups)
+    if func in ("max", "len"):
+        np.testing.assert_array_equal(ref, want)
+    else:
+        np.testing.assert_allclose(ref, want, rtol=1e-6)
